@@ -1,0 +1,634 @@
+// libsangnom_cuda C ABI (include/sangnom_cuda.h): context, streams, staging, frame planning.
+//
+// Host-side counterpart of the reference's GetFrame plane loop (/root/reference/src/
+// SangNom2.cpp:346-394) for a BATCH of frames: kept-field upload (the BitBlt at :361-377 becomes
+// a strided H2D copy straight into the device plane), the per-plane `process` call (:393) becomes
+// one thread block of the row-sweep kernel, and the finished planes are copied back.
+// There is no CPU compute path in this file: without a CUDA device every call fails.
+#include "sangnom_cuda.h"
+#include "sangnom_kernels.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t need)
+    {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        need = (need + 0xFFFFF) & ~(size_t)0xFFFFF;   // 1 MiB granules
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t need)
+    {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; bytes = 0;
+        need = (need + 0xFFFFF) & ~(size_t)0xFFFFF;
+        cudaError_t e = cudaHostAlloc(&p, need, cudaHostAllocDefault);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+};
+
+// A processed plane of one frame, after validation.
+struct Pass {
+    const sn_plane_job* job;
+    int W, H, n;             // samples, rows, kept rows
+    int R;                   // pool rows to sweep
+    sn::CostState in{}, out{};
+    // device placement (host path)
+    size_t dev_off = 0;      // byte offset of the plane inside the chunk's plane buffer
+    size_t dev_pitch = 0;    // bytes
+    // staging placement for pageable host memory
+    size_t stage_in_off = 0, stage_out_off = 0;
+    bool src_pinned = false, dst_pinned = false;
+};
+
+struct FramePlan {
+    int key;
+    std::vector<Pass> passes;            // processed planes in plane order (at most 3)
+    std::vector<const sn_plane_job*> copies;
+    size_t state_bytes = 0;              // cost-state scratch of this frame
+    size_t state_off = 0;
+};
+
+// One pipeline slot: a chunk of frames resident on the device.
+struct Slot {
+    DevBuf planes, state, tasks;
+    PinnedBuf tasks_host, stage_in, stage_out;
+    cudaStream_t compute = nullptr;
+    cudaEvent_t h2d_done = nullptr, kernels_done = nullptr, d2h_done = nullptr;
+    bool busy = false;
+    std::vector<FramePlan*> frames;      // frames of the chunk in flight (for the pageable copy-out)
+};
+
+constexpr int kSlots = 3;
+constexpr int kTaskRing = 8;
+
+}  // namespace
+
+struct sn_ctx {
+    sn_config cfg{};
+    int sample_bytes = 1;
+    int S = 0, Hb = 0;
+    int frames_in_flight = 0;
+    cudaStream_t h2d = nullptr, d2h = nullptr, own_compute = nullptr;
+    Slot slots[kSlots];
+    // device-entry resources
+    DevBuf dev_state;
+    DevBuf dev_tasks[kTaskRing];
+    PinnedBuf dev_tasks_host[kTaskRing];
+    cudaEvent_t dev_task_free[kTaskRing] = {};
+    int dev_ring_pos = 0;
+    sn_stats stats{};
+    std::string error;
+    std::mutex mu;
+
+    int fail(int code, const char* fmt, ...)
+    {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        error = buf;
+        return code;
+    }
+    int cuda_fail(cudaError_t e, const char* what)
+    {
+        return fail(SN_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    }
+};
+
+#define SN_CUDA(ctx, call)                                          \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) return (ctx)->cuda_fail(e__, #call); \
+    } while (0)
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+bool is_pinned_host(const void* p)
+{
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// Group jobs into frames, validate, and derive for every processed plane how many pool rows its
+// pass must sweep and which blurred cost cells it has to hand to the next pass.
+//
+// Reference behaviour being reproduced: every plane's cost recursion runs over the whole pool
+// (rows 1..Hb-1, all S columns; SangNom2.cpp:133-136,269-270) while only rows 1..n-1, cols < W are
+// freshly written for that plane (:79-81). So pass q reads, outside its own rectangle, what pass
+// q-1 left there - itself the result of q-1's recursion over what q-2 left, and so on. A cell
+// pass q reads at pool row r must therefore have been swept by every earlier pass of the frame.
+int plan_frames(sn_ctx* ctx, const sn_plane_job* jobs, int njobs, bool device_entry, std::vector<FramePlan>& frames)
+{
+    const int sb = ctx->sample_bytes;
+    std::map<int, size_t> index;
+    for (int j = 0; j < njobs; ++j) {
+        const sn_plane_job& jb = jobs[j];
+        if (jb.width <= 0 || jb.dst_height <= 0) return ctx->fail(SN_ERR_INVALID, "job %d: empty plane", j);
+        if (jb.plane < 0 || jb.plane > 3) return ctx->fail(SN_ERR_INVALID, "job %d: plane index %d", j, jb.plane);
+        if (!jb.dst || (jb.mode != SN_MODE_INPLACE && !jb.src)) return ctx->fail(SN_ERR_INVALID, "job %d: null pointer", j);
+        if (jb.mode == SN_MODE_INPLACE && !device_entry) return ctx->fail(SN_ERR_INVALID, "job %d: SN_MODE_INPLACE needs the device entry", j);
+        if (jb.mode < SN_MODE_COPY || jb.mode > SN_MODE_INPLACE) return ctx->fail(SN_ERR_INVALID, "job %d: mode %d", j, jb.mode);
+        const ptrdiff_t row_bytes = (ptrdiff_t)jb.width * sb;
+        if (jb.dst_pitch < row_bytes || (jb.mode != SN_MODE_INPLACE && jb.src_pitch < row_bytes))
+            return ctx->fail(SN_ERR_INVALID, "job %d: pitch smaller than a row", j);
+        if (jb.dst_pitch % sb != 0) return ctx->fail(SN_ERR_INVALID, "job %d: pitch not a multiple of the sample size", j);
+        auto it = index.find(jb.frame);
+        if (it == index.end()) {
+            it = index.emplace(jb.frame, frames.size()).first;
+            frames.emplace_back();
+            frames.back().key = jb.frame;
+        }
+        FramePlan& f = frames[it->second];
+        if (jb.mode == SN_MODE_COPY) { f.copies.push_back(&jb); continue; }
+        if (jb.offset != 0 && jb.offset != 1) return ctx->fail(SN_ERR_INVALID, "job %d: offset %d", j, jb.offset);
+        if (jb.dst_height % 2 != 0) return ctx->fail(SN_ERR_INVALID, "job %d: dst_height must be even", j);
+        if (jb.width > ctx->S) return ctx->fail(SN_ERR_INVALID, "job %d: width %d exceeds the pool width %d", j, jb.width, ctx->S);
+        if (jb.dst_height / 2 > ctx->Hb) return ctx->fail(SN_ERR_INVALID, "job %d: height %d exceeds the pool height", j, jb.dst_height);
+        if (jb.plane == 3) return ctx->fail(SN_ERR_INVALID, "job %d: the alpha plane is never interpolated; use SN_MODE_COPY", j);
+        Pass p{};
+        p.job = &jb;
+        p.W = jb.width; p.H = jb.dst_height; p.n = jb.dst_height / 2;
+        for (const Pass& q : f.passes)
+            if (q.job->plane == jb.plane) return ctx->fail(SN_ERR_INVALID, "frame %d: plane %d given twice", jb.frame, jb.plane);
+        f.passes.push_back(p);
+    }
+    const int S = ctx->S, Hb = ctx->Hb;
+    for (FramePlan& f : frames) {
+        std::stable_sort(f.passes.begin(), f.passes.end(), [](const Pass& a, const Pass& b) { return a.job->plane < b.job->plane; });
+        const int m = (int)f.passes.size();
+        for (int q = m - 1; q >= 0; --q) {
+            Pass& p = f.passes[q];
+            p.R = std::min(p.n - 1, Hb - 1);
+            if (q + 1 < m) p.R = std::max(p.R, std::min(Hb - 1, f.passes[q + 1].R + 1));
+        }
+        // cost state handed from pass q to pass q+1
+        size_t off = 0;
+        for (int q = 0; q + 1 < m; ++q) {
+            Pass& p = f.passes[q];
+            const Pass& nx = f.passes[q + 1];
+            sn::CostState st{};
+            // region A: rows inside the next pass's row range, columns right of its rectangle
+            const int a_rows = std::min(nx.n - 1, p.R);
+            if (nx.W < S && a_rows >= 1) {
+                st.a_x0 = nx.W; st.a_rows = a_rows;
+                st.a = reinterpret_cast<void*>(off + 1);   // offset+1 for now (0 means empty); fixed up at placement
+                off += align_up((size_t)sn::kNumCost * (a_rows + 1) * (S - nx.W) * sb, 256);
+            }
+            // region B: rows below the next pass's rectangle that its recursion still reads
+            const int b0 = std::max(nx.n, 1), b1 = std::min(std::min(nx.R + 1, Hb - 1), p.R);
+            if (b1 >= b0) {
+                st.b_r0 = b0; st.b_r1 = b1;
+                st.b = reinterpret_cast<void*>(off + 1);
+                off += align_up((size_t)sn::kNumCost * (b1 - b0 + 1) * S * sb, 256);
+            }
+            p.out = st;
+            f.passes[q + 1].in = st;
+        }
+        f.state_bytes = off;
+    }
+    return SN_OK;
+}
+
+void place_state(FramePlan& f, char* base)
+{
+    auto fix = [&](sn::CostState& s) {
+        if (s.a) s.a = base + (reinterpret_cast<size_t>(s.a) - 1);
+        if (s.b) s.b = base + (reinterpret_cast<size_t>(s.b) - 1);
+    };
+    for (Pass& p : f.passes) { fix(p.in); fix(p.out); }
+}
+
+sn::PlaneTask make_task(const sn_ctx* ctx, const Pass& p, void* plane, size_t pitch_bytes)
+{
+    sn::PlaneTask t{};
+    t.plane = plane;
+    t.pitch = (long long)(pitch_bytes / ctx->sample_bytes);
+    t.width = p.W; t.height = p.H; t.offset = p.job->offset;
+    t.kept_rows = p.n; t.sweep_rows = p.R;
+    t.thr_f = p.job->threshold;
+    // `const T aaf` (reference SangNom2.cpp:162,272): float -> T truncation for integer samples
+    if (ctx->sample_bytes == 1) t.thr_i = (int)(uint8_t)p.job->threshold;
+    else if (ctx->sample_bytes == 2) t.thr_i = (int)(uint16_t)p.job->threshold;
+    t.in = p.in; t.out = p.out;
+    return t;
+}
+
+void host_copy_plane(const sn_plane_job& jb, int sb)
+{
+    if (jb.src == jb.dst) return;
+    const size_t row = (size_t)jb.width * sb;
+    for (int y = 0; y < jb.dst_height; ++y)
+        std::memcpy(static_cast<char*>(jb.dst) + (ptrdiff_t)y * jb.dst_pitch, static_cast<const char*>(jb.src) + (ptrdiff_t)y * jb.src_pitch, row);
+}
+
+// Launch the passes of a set of frames: one kernel per pass index (all first planes, then all
+// second planes, ...), stream-ordered so pass q+1 of a frame sees pass q's cost state.
+int launch_passes(sn_ctx* ctx, const std::vector<std::vector<sn::PlaneTask>>& by_pass, sn::PlaneTask* host_tasks,
+                  sn::PlaneTask* dev_tasks, cudaStream_t stream)
+{
+    size_t total = 0;
+    for (auto& v : by_pass) { std::memcpy(host_tasks + total, v.data(), v.size() * sizeof(sn::PlaneTask)); total += v.size(); }
+    if (total == 0) return SN_OK;
+    SN_CUDA(ctx, cudaMemcpyAsync(dev_tasks, host_tasks, total * sizeof(sn::PlaneTask), cudaMemcpyHostToDevice, stream));
+    size_t pos = 0;
+    for (auto& v : by_pass) {
+        if (v.empty()) continue;
+        SN_CUDA(ctx, sn::launch_plane_tasks(ctx->sample_bytes, dev_tasks + pos, (int)v.size(), sn::LaunchGeometry{ ctx->S, ctx->Hb }, stream));
+        ctx->stats.kernel_launches += 1;
+        ctx->stats.planes_processed += v.size();
+        pos += v.size();
+    }
+    return SN_OK;
+}
+
+// Copy the finished planes of a chunk from pinned staging to pageable destinations.
+int drain_slot(sn_ctx* ctx, Slot& s)
+{
+    if (!s.busy) return SN_OK;
+    SN_CUDA(ctx, cudaEventSynchronize(s.d2h_done));
+    const int sb = ctx->sample_bytes;
+    for (FramePlan* f : s.frames)
+        for (Pass& p : f->passes) {
+            if (p.dst_pinned) continue;
+            const sn_plane_job& jb = *p.job;
+            const size_t row = (size_t)p.W * sb;
+            const char* st = static_cast<const char*>(s.stage_out.p) + p.stage_out_off;
+            for (int y = 0; y < p.H; ++y) std::memcpy(static_cast<char*>(jb.dst) + (ptrdiff_t)y * jb.dst_pitch, st + (size_t)y * row, row);
+        }
+    s.frames.clear();
+    s.busy = false;
+    return SN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sangnom_cuda_abi_version(void) { return SANGNOM_CUDA_ABI_VERSION; }
+
+const char* sangnom_cuda_last_error(sn_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+float sangnom_cuda_threshold(int aa, int bits, int sample_type)
+{
+    // float arithmetic in the reference's order (SangNom2.cpp:282)
+    if (sample_type < 4) return (aa * 21.0f / 16.0f) * (float)(1 << (bits - 8));
+    return (aa * 21.0f / 16.0f) / 256.0f;
+}
+
+int sangnom_cuda_get_limits(int device, sn_limits* out)
+{
+    if (!out) return SN_ERR_INVALID;
+    std::memset(out, 0, sizeof *out);
+    cudaDeviceProp prop{};
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e); return SN_ERR_CUDA; }
+    out->max_pool_width[1] = sn::max_pool_width(1);
+    out->max_pool_width[2] = sn::max_pool_width(2);
+    out->max_pool_width[4] = sn::max_pool_width(4);
+    out->sm_count = prop.multiProcessorCount;
+    out->compute_major = prop.major;
+    out->compute_minor = prop.minor;
+    return SN_OK;
+}
+
+void* sangnom_cuda_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void sangnom_cuda_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int sangnom_cuda_create(const sn_config* cfg, sn_ctx** out)
+{
+    if (!cfg || !out) { g_create_error = "null argument"; return SN_ERR_INVALID; }
+    *out = nullptr;
+    if (cfg->abi_version != SANGNOM_CUDA_ABI_VERSION) { g_create_error = "ABI version mismatch"; return SN_ERR_INVALID; }
+    if (cfg->sample_type != SN_SAMPLE_U8 && cfg->sample_type != SN_SAMPLE_U16 && cfg->sample_type != SN_SAMPLE_F32) {
+        g_create_error = "sample_type must be 1, 2 or 4"; return SN_ERR_INVALID;
+    }
+    if (cfg->pool_width <= 0 || cfg->pool_height <= 0) { g_create_error = "pool dimensions must be positive"; return SN_ERR_INVALID; }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (libsangnom_cuda has no CPU path)";
+        cudaGetLastError();
+        return SN_ERR_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= count) { g_create_error = "device ordinal out of range"; return SN_ERR_INVALID; }
+    cudaDeviceProp prop{};
+    e = cudaGetDeviceProperties(&prop, cfg->device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return SN_ERR_CUDA; }
+    if (prop.major != 10) {
+        char b[160];
+        snprintf(b, sizeof b, "device %d is sm_%d%d; this library carries sm_100a code only", cfg->device, prop.major, prop.minor);
+        g_create_error = b;
+        return SN_ERR_CUDA;
+    }
+    const int S = (cfg->pool_width + 31) & ~31;               // reference SangNom2.cpp:287
+    const int Hb = (cfg->pool_height + 1) >> 1;               // reference SangNom2.cpp:288
+    if (S > sn::max_pool_width(cfg->sample_type)) {
+        char b[160];
+        snprintf(b, sizeof b, "pool width %d exceeds the supported maximum %d for %d-byte samples", S, sn::max_pool_width(cfg->sample_type), cfg->sample_type);
+        g_create_error = b;
+        return SN_ERR_UNSUPPORTED;
+    }
+    sn_ctx* ctx = new sn_ctx();
+    ctx->cfg = *cfg;
+    ctx->sample_bytes = cfg->sample_type;
+    ctx->S = S; ctx->Hb = Hb;
+    ctx->frames_in_flight = cfg->max_frames_in_flight > 0 ? cfg->max_frames_in_flight : 96;
+    auto bail = [&](cudaError_t err, const char* what) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        sangnom_cuda_destroy(ctx);
+        return SN_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    if ((e = cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_compute, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    for (Slot& s : ctx->slots) {
+        if ((e = cudaStreamCreateWithFlags(&s.compute, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+        if ((e = cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+        if ((e = cudaEventCreateWithFlags(&s.kernels_done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+        if ((e = cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    }
+    for (int i = 0; i < kTaskRing; ++i)
+        if ((e = cudaEventCreateWithFlags(&ctx->dev_task_free[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    *out = ctx;
+    return SN_OK;
+}
+
+void sangnom_cuda_destroy(sn_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    cudaDeviceSynchronize();
+    for (Slot& s : ctx->slots) {
+        s.planes.release(); s.state.release(); s.tasks.release();
+        s.tasks_host.release(); s.stage_in.release(); s.stage_out.release();
+        if (s.compute) cudaStreamDestroy(s.compute);
+        if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+        if (s.kernels_done) cudaEventDestroy(s.kernels_done);
+        if (s.d2h_done) cudaEventDestroy(s.d2h_done);
+    }
+    ctx->dev_state.release();
+    for (int i = 0; i < kTaskRing; ++i) {
+        ctx->dev_tasks[i].release();
+        ctx->dev_tasks_host[i].release();
+        if (ctx->dev_task_free[i]) cudaEventDestroy(ctx->dev_task_free[i]);
+    }
+    if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
+    if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
+    if (ctx->own_compute) cudaStreamDestroy(ctx->own_compute);
+    cudaGetLastError();
+    delete ctx;
+}
+
+int sangnom_cuda_get_stats(sn_ctx* ctx, sn_stats* out)
+{
+    if (!ctx || !out) return SN_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    *out = ctx->stats;
+    return SN_OK;
+}
+
+void sangnom_cuda_reset_stats(sn_ctx* ctx)
+{
+    if (!ctx) return;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->stats = sn_stats{};
+}
+
+int sangnom_cuda_synchronize(sn_ctx* ctx)
+{
+    if (!ctx) return SN_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SN_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    SN_CUDA(ctx, cudaStreamSynchronize(ctx->own_compute));
+    return SN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int sangnom_cuda_process_planes_device(sn_ctx* ctx, const sn_plane_job* jobs, int njobs, void* cuda_stream)
+{
+    if (!ctx) return SN_ERR_INVALID;
+    if (njobs < 0 || (njobs > 0 && !jobs)) return ctx->fail(SN_ERR_INVALID, "bad job list");
+    if (njobs == 0) return SN_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SN_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaStream_t stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_compute;
+    const int sb = ctx->sample_bytes;
+
+    std::vector<FramePlan> frames;
+    int rc = plan_frames(ctx, jobs, njobs, true, frames);
+    if (rc != SN_OK) return rc;
+
+    size_t state_total = 0, ntasks = 0;
+    for (FramePlan& f : frames) { f.state_off = state_total; state_total += align_up(f.state_bytes, 256); ntasks += f.passes.size(); }
+    // The scratch is shared by all device calls of this context: they must be stream-ordered.
+    if (state_total > ctx->dev_state.bytes) {
+        SN_CUDA(ctx, cudaStreamSynchronize(stream));
+        SN_CUDA(ctx, ctx->dev_state.ensure(state_total));
+    }
+
+    // plane copies / kept-field placement
+    for (FramePlan& f : frames) {
+        for (const sn_plane_job* c : f.copies) {
+            if (c->src == c->dst) continue;
+            SN_CUDA(ctx, cudaMemcpy2DAsync(c->dst, (size_t)c->dst_pitch, c->src, (size_t)c->src_pitch, (size_t)c->width * sb,
+                                           (size_t)c->dst_height, cudaMemcpyDeviceToDevice, stream));
+        }
+        place_state(f, static_cast<char*>(ctx->dev_state.p) + f.state_off);
+        for (Pass& p : f.passes) {
+            const sn_plane_job& jb = *p.job;
+            if (jb.mode == SN_MODE_INPLACE) continue;
+            const char* src = static_cast<const char*>(jb.src) + (jb.mode == SN_MODE_FIELD ? (ptrdiff_t)jb.offset * jb.src_pitch : 0);
+            const size_t spitch = (size_t)jb.src_pitch * (jb.mode == SN_MODE_FIELD ? 2 : 1);
+            char* dst = static_cast<char*>(jb.dst) + (ptrdiff_t)jb.offset * jb.dst_pitch;
+            if (src != dst)
+                SN_CUDA(ctx, cudaMemcpy2DAsync(dst, (size_t)jb.dst_pitch * 2, src, spitch, (size_t)p.W * sb, (size_t)p.n,
+                                               cudaMemcpyDeviceToDevice, stream));
+        }
+    }
+
+    std::vector<std::vector<sn::PlaneTask>> by_pass(3);
+    for (FramePlan& f : frames)
+        for (size_t q = 0; q < f.passes.size(); ++q)
+            by_pass[q].push_back(make_task(ctx, f.passes[q], f.passes[q].job->dst, (size_t)f.passes[q].job->dst_pitch));
+
+    const int slot = ctx->dev_ring_pos;
+    ctx->dev_ring_pos = (ctx->dev_ring_pos + 1) % kTaskRing;
+    SN_CUDA(ctx, cudaEventSynchronize(ctx->dev_task_free[slot]));     // ring entry no longer read by an earlier upload
+    SN_CUDA(ctx, ctx->dev_tasks_host[slot].ensure(ntasks * sizeof(sn::PlaneTask)));
+    if (ntasks * sizeof(sn::PlaneTask) > ctx->dev_tasks[slot].bytes) {
+        SN_CUDA(ctx, cudaStreamSynchronize(stream));
+        SN_CUDA(ctx, ctx->dev_tasks[slot].ensure(ntasks * sizeof(sn::PlaneTask)));
+    }
+    rc = launch_passes(ctx, by_pass, static_cast<sn::PlaneTask*>(ctx->dev_tasks_host[slot].p),
+                       static_cast<sn::PlaneTask*>(ctx->dev_tasks[slot].p), stream);
+    if (rc != SN_OK) return rc;
+    SN_CUDA(ctx, cudaEventRecord(ctx->dev_task_free[slot], stream));
+    ctx->stats.frames += frames.size();
+    return SN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs)
+{
+    if (!ctx) return SN_ERR_INVALID;
+    if (njobs < 0 || (njobs > 0 && !jobs)) return ctx->fail(SN_ERR_INVALID, "bad job list");
+    if (njobs == 0) return SN_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SN_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const int sb = ctx->sample_bytes;
+
+    std::vector<FramePlan> frames;
+    int rc = plan_frames(ctx, jobs, njobs, false, frames);
+    if (rc != SN_OK) return rc;
+
+    // classify host pointers once per distinct allocation is not possible in general; per job is fine
+    for (FramePlan& f : frames)
+        for (Pass& p : f.passes) {
+            p.src_pinned = is_pinned_host(p.job->src);
+            p.dst_pinned = is_pinned_host(p.job->dst);
+        }
+
+    const size_t chunk_frames = std::max<size_t>(1, (size_t)ctx->frames_in_flight / kSlots);
+    size_t next = 0;
+    int slot_idx = 0;
+    int status = SN_OK;
+    while (next < frames.size() && status == SN_OK) {
+        Slot& s = ctx->slots[slot_idx];
+        slot_idx = (slot_idx + 1) % kSlots;
+        if ((status = drain_slot(ctx, s)) != SN_OK) break;     // also guarantees the slot's device buffers are free
+
+        const size_t first = next, last = std::min(frames.size(), next + chunk_frames);
+        next = last;
+
+        // placement inside the slot
+        size_t plane_bytes = 0, state_bytes = 0, in_bytes = 0, out_bytes = 0, ntasks = 0;
+        for (size_t k = first; k < last; ++k) {
+            FramePlan& f = frames[k];
+            f.state_off = state_bytes;
+            state_bytes += align_up(f.state_bytes, 256);
+            for (Pass& p : f.passes) {
+                p.dev_pitch = align_up((size_t)p.W * sb, 256);
+                p.dev_off = plane_bytes;
+                plane_bytes += p.dev_pitch * p.H;
+                if (!p.src_pinned) { p.stage_in_off = in_bytes; in_bytes += align_up((size_t)p.W * sb * p.n, 256); }
+                if (!p.dst_pinned) { p.stage_out_off = out_bytes; out_bytes += align_up((size_t)p.W * sb * p.H, 256); }
+                ++ntasks;
+            }
+        }
+        cudaError_t e;
+        if ((e = s.planes.ensure(plane_bytes)) != cudaSuccess || (e = s.state.ensure(state_bytes)) != cudaSuccess ||
+            (e = s.tasks.ensure(ntasks * sizeof(sn::PlaneTask))) != cudaSuccess ||
+            (e = s.tasks_host.ensure(ntasks * sizeof(sn::PlaneTask))) != cudaSuccess ||
+            (e = s.stage_in.ensure(in_bytes)) != cudaSuccess || (e = s.stage_out.ensure(out_bytes)) != cudaSuccess) {
+            status = ctx->cuda_fail(e, "slot allocation");
+            break;
+        }
+
+        // ---- upload the kept fields (the reference's BitBlt :361-377, as a strided DMA) ----
+        std::vector<std::vector<sn::PlaneTask>> by_pass(3);
+        for (size_t k = first; k < last && status == SN_OK; ++k) {
+            FramePlan& f = frames[k];
+            for (const sn_plane_job* c : f.copies) host_copy_plane(*c, sb);
+            place_state(f, static_cast<char*>(s.state.p) + f.state_off);
+            for (size_t q = 0; q < f.passes.size(); ++q) {
+                Pass& p = f.passes[q];
+                const sn_plane_job& jb = *p.job;
+                const size_t row = (size_t)p.W * sb;
+                const char* src = static_cast<const char*>(jb.src) + (jb.mode == SN_MODE_FIELD ? (ptrdiff_t)jb.offset * jb.src_pitch : 0);
+                size_t spitch = (size_t)jb.src_pitch * (jb.mode == SN_MODE_FIELD ? 2 : 1);
+                if (!p.src_pinned) {
+                    char* st = static_cast<char*>(s.stage_in.p) + p.stage_in_off;
+                    for (int y = 0; y < p.n; ++y) std::memcpy(st + (size_t)y * row, src + (size_t)y * spitch, row);
+                    src = st; spitch = row;
+                }
+                char* dplane = static_cast<char*>(s.planes.p) + p.dev_off;
+                e = cudaMemcpy2DAsync(dplane + (size_t)jb.offset * p.dev_pitch, p.dev_pitch * 2, src, spitch, row, (size_t)p.n,
+                                      cudaMemcpyHostToDevice, ctx->h2d);
+                if (e != cudaSuccess) { status = ctx->cuda_fail(e, "H2D copy"); break; }
+                ctx->stats.h2d_bytes += row * p.n;
+                by_pass[q].push_back(make_task(ctx, p, dplane, p.dev_pitch));
+            }
+        }
+        if (status != SN_OK) break;
+        if ((e = cudaEventRecord(s.h2d_done, ctx->h2d)) != cudaSuccess || (e = cudaStreamWaitEvent(s.compute, s.h2d_done, 0)) != cudaSuccess) {
+            status = ctx->cuda_fail(e, "event"); break;
+        }
+
+        // ---- kernels ----
+        status = launch_passes(ctx, by_pass, static_cast<sn::PlaneTask*>(s.tasks_host.p), static_cast<sn::PlaneTask*>(s.tasks.p), s.compute);
+        if (status != SN_OK) break;
+        if ((e = cudaEventRecord(s.kernels_done, s.compute)) != cudaSuccess || (e = cudaStreamWaitEvent(ctx->d2h, s.kernels_done, 0)) != cudaSuccess) {
+            status = ctx->cuda_fail(e, "event"); break;
+        }
+
+        // ---- download ----
+        for (size_t k = first; k < last && status == SN_OK; ++k) {
+            FramePlan& f = frames[k];
+            for (Pass& p : f.passes) {
+                const sn_plane_job& jb = *p.job;
+                const size_t row = (size_t)p.W * sb;
+                char* dst = static_cast<char*>(jb.dst);
+                size_t dpitch = (size_t)jb.dst_pitch;
+                if (!p.dst_pinned) { dst = static_cast<char*>(s.stage_out.p) + p.stage_out_off; dpitch = row; }
+                e = cudaMemcpy2DAsync(dst, dpitch, static_cast<char*>(s.planes.p) + p.dev_off, p.dev_pitch, row, (size_t)p.H,
+                                      cudaMemcpyDeviceToHost, ctx->d2h);
+                if (e != cudaSuccess) { status = ctx->cuda_fail(e, "D2H copy"); break; }
+                ctx->stats.d2h_bytes += row * p.H;
+            }
+            s.frames.push_back(&f);
+        }
+        if (status != SN_OK) break;
+        if ((e = cudaEventRecord(s.d2h_done, ctx->d2h)) != cudaSuccess) { status = ctx->cuda_fail(e, "event"); break; }
+        s.busy = true;
+        ctx->stats.frames += last - first;
+    }
+    // drain everything (in submission order) even on error so no copy is left writing user memory
+    for (int k = 0; k < kSlots; ++k) {
+        Slot& s = ctx->slots[(slot_idx + k) % kSlots];
+        if (status == SN_OK) status = drain_slot(ctx, s);
+        else { cudaEventSynchronize(s.d2h_done); s.frames.clear(); s.busy = false; }
+    }
+    if (status != SN_OK) { cudaStreamSynchronize(ctx->h2d); cudaStreamSynchronize(ctx->d2h); cudaGetLastError(); }
+    return status;
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+// Internal interface between the C-ABI layer (sangnom_api.cu) and the kernels (sangnom_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sn {
+
+constexpr int kNumCost = 9;   // the nine direction-cost buffers (reference SangNom2.h:8-24)
+
+// Cost state handed from one plane pass of a frame to the next. It stands in for what the
+// reference's shared, never-cleared scratch pool holds outside the next plane's rectangle
+// (reference SangNom2.cpp:79-81 writes only rows 1..h/2-1, cols < w; :133-136 re-blurs all of it).
+//   region A: pool rows 1..a_rows, pool columns [a_x0, S)      stored [9][a_rows+1][S-a_x0]
+//   region B: pool rows b_r0..b_r1, all S columns              stored [9][b_r1-b_r0+1][S]
+// Cells outside both regions read as 0 (the zero-filled pool of the parity contract).
+struct CostState {
+    void* a;        // nullptr = region empty
+    void* b;
+    int a_x0, a_rows;
+    int b_r0, b_r1;
+};
+
+// One plane pass = one thread block sweeping pool rows 1..sweep_rows over all S pool columns.
+struct PlaneTask {
+    void* plane;            // device pointer to row 0 of the dst plane (kept field already in place)
+    long long pitch;        // elements
+    int width;              // W: samples per row that carry pixels (cost rectangle width)
+    int height;             // H: rows of the dst plane
+    int offset;             // 0 / 1: first kept row
+    int kept_rows;          // n = H/2
+    int sweep_rows;         // R >= n-1: pool rows to run the cost recursion over
+    int thr_i;              // threshold truncated to the sample type (integer flavours)
+    float thr_f;            // fp32 flavour
+    CostState in, out;      // cost state from the previous pass / for the next pass of this frame
+};
+
+struct LaunchGeometry {
+    int S;                  // pool row length in samples (align32 of the output luma width)
+    int Hb;                 // pool rows: (output luma height + 1) >> 1
+};
+
+// Widest pool each sample type can run (columns per thread x max threads per block).
+int max_pool_width(int sample_bytes);
+
+// Launch one block per task. `tasks_dev` is a device array of ntasks PlaneTask.
+// Returns cudaSuccess or the launch error. sample_bytes in {1,2,4}.
+cudaError_t launch_plane_tasks(int sample_bytes, const PlaneTask* tasks_dev, int ntasks, LaunchGeometry g,
+                               cudaStream_t stream);
+
+// Name of the kernel variant launch_plane_tasks would use (for logs / profiles).
+const char* kernel_variant_name(int sample_bytes, int S);
+
+}  // namespace sn

@@ -1,0 +1,150 @@
+/*
+ * sangnom_cuda.h - C ABI of libsangnom_cuda: SangNom2's edge-directed field interpolation on
+ * NVIDIA B200 (sm_100a only; there is no CPU fallback - every entry point fails with
+ * SN_ERR_CUDA when no usable device is present).
+ *
+ * This is the drop-in seam for the reference's per-plane hot path. Each entry point names the
+ * reference interface it replaces (paths relative to /root/reference):
+ *
+ *   sangnom_cuda_create / _destroy
+ *       replaces the scratch-pool half of SangNom2::SangNom2 (src/SangNom2.cpp:287-310: pool
+ *       geometry bufferStride/bufferHeight from the OUTPUT luma size, pool + line allocation) and
+ *       the implicit free in ~SangNom2 (src/SangNom2.h:50-51). The context owns the CUDA streams,
+ *       pinned staging, device planes and the inter-plane cost-state scratch.
+ *   sangnom_cuda_process_planes
+ *       replaces, for a batch of planes, the body of the plane loop in SangNom2::GetFrame
+ *       (src/SangNom2.cpp:348-394): the kept-field copy (:361-377), the un-interpolatable border
+ *       row copy (:380-391) and the call through the `process` member pointer (:393), i.e.
+ *       sangnom_c<T,IType> (:259-273) = prepareBuffers_c (:74-124) + 9 x processBuffers_c
+ *       (:126-159) + finalizePlane_c (:161-257).
+ *   sangnom_cuda_process_planes_device
+ *       the same seam for planes already resident in device memory (no PCIe copies), in place
+ *       exactly like `process(dstp, dstStride, w, h, offset, plane)` (:393).
+ *   sangnom_cuda_threshold
+ *       replaces the aaf[] scaling in the ctor (src/SangNom2.cpp:280-282).
+ *
+ * Numerics contract: results are bit-identical to the reference's opt=0 C++ path for 8..16-bit
+ * integer samples and for fp32 (same operation order, no FMA contraction), under the rule
+ * "each frame is processed as by a freshly constructed filter instance whose scratch pool is
+ * zero-filled, planes in Y,U,V order" (DESIGN.md, section Parity contract). The coupling of the
+ * U and V planes to the luma cost state that the reference's shared pool produces is reproduced
+ * exactly; that is why jobs carry a frame key.
+ */
+#ifndef SANGNOM_CUDA_H
+#define SANGNOM_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SN_API __attribute__((visibility("default")))
+#else
+#define SN_API
+#endif
+
+#define SANGNOM_CUDA_ABI_VERSION 1
+
+typedef struct sn_ctx sn_ctx;
+
+enum sn_status {
+    SN_OK = 0,
+    SN_ERR_INVALID = 1,      /* bad argument / inconsistent job list */
+    SN_ERR_CUDA = 2,         /* CUDA runtime error or no sm_100 device */
+    SN_ERR_UNSUPPORTED = 3,  /* geometry outside what the kernels cover (see sn_limits) */
+    SN_ERR_NOMEM = 4
+};
+
+enum sn_sample {             /* == bytes per sample == AviSynth ComponentSize() */
+    SN_SAMPLE_U8 = 1,
+    SN_SAMPLE_U16 = 2,       /* 10/12/14/16-bit ride in 16-bit containers */
+    SN_SAMPLE_F32 = 4
+};
+
+enum sn_mode {
+    SN_MODE_COPY = 0,        /* plane not processed: dst := src (disabled plane, alpha) (:369-374) */
+    SN_MODE_FIELD = 1,       /* src is a full-height plane; rows offset,offset+2,.. are kept (:376) */
+    SN_MODE_DH = 2,          /* src has dst_height/2 rows; they become rows offset,offset+2,.. (:361-366) */
+    SN_MODE_INPLACE = 3      /* device entry only: dst already holds the kept field; src ignored (:393) */
+};
+
+typedef struct sn_config {
+    int abi_version;         /* SANGNOM_CUDA_ABI_VERSION */
+    int device;              /* CUDA device ordinal */
+    int sample_type;         /* enum sn_sample */
+    int pool_width;          /* OUTPUT luma width in samples  (vi.width)            -> S  = align32 */
+    int pool_height;         /* OUTPUT luma height in rows    (vi.height after dh)  -> Hb = (h+1)>>1 */
+    int max_frames_in_flight;/* frames resident on the device at once (0 = library default) */
+    int flags;               /* reserved, 0 */
+} sn_config;
+
+/* One plane of one frame. Pitches are in BYTES. */
+typedef struct sn_plane_job {
+    const void* src;
+    ptrdiff_t src_pitch;
+    void* dst;
+    ptrdiff_t dst_pitch;
+    int width;               /* samples per row */
+    int dst_height;          /* rows of the dst plane (src has dst_height rows, or dst_height/2 for DH) */
+    int offset;              /* 0: keep rows 0,2,4.. (top field)  1: keep rows 1,3,5.. */
+    int mode;                /* enum sn_mode */
+    float threshold;         /* sangnom_cuda_threshold(aa or aac, bits, sample_type) */
+    int plane;               /* 0 Y, 1 U, 2 V, 3 A - processing order inside a frame is by this index */
+    int frame;               /* caller's key: jobs with equal key belong to one frame and share one
+                                (virtual) scratch pool, exactly like one GetFrame call */
+} sn_plane_job;
+
+typedef struct sn_limits {
+    int max_pool_width[5];   /* indexed by sample bytes (1,2,4): widest pool the kernels accept */
+    int sm_count;
+    int compute_major, compute_minor;
+} sn_limits;
+
+typedef struct sn_stats {    /* counters since create (or the last reset) */
+    uint64_t kernel_launches;
+    uint64_t planes_processed;
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t frames;
+} sn_stats;
+
+/* Create a context on cfg->device. Returns SN_OK and *out, or an error (message via
+ * sangnom_cuda_last_error(NULL)). */
+SN_API int sangnom_cuda_create(const sn_config* cfg, sn_ctx** out);
+SN_API void sangnom_cuda_destroy(sn_ctx* ctx);
+
+/* HOST buffers. Pinned (cudaHostAlloc / cudaHostRegister) buffers are DMA'd directly; pageable
+ * buffers go through the context's pinned staging. Jobs may be in any order; they are grouped by
+ * `frame` and run in plane order. Synchronous: returns when every dst is complete. Frames are
+ * pipelined internally (H2D | kernels | D2H on three streams). */
+SN_API int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs);
+
+/* DEVICE buffers: src/dst are device pointers on ctx's device. Asynchronous on `cuda_stream`
+ * (a cudaStream_t passed as void*; NULL = the context's compute stream); no host/device copies.
+ * The job list is consumed before the call returns. */
+SN_API int sangnom_cuda_process_planes_device(sn_ctx* ctx, const sn_plane_job* jobs, int njobs, void* cuda_stream);
+
+/* Block until everything queued by _device on the context's own stream has finished. */
+SN_API int sangnom_cuda_synchronize(sn_ctx* ctx);
+
+/* aa/aac (0..128) -> threshold in sample units, float arithmetic as SangNom2.cpp:280-282. */
+SN_API float sangnom_cuda_threshold(int aa, int bits_per_component, int sample_type);
+
+SN_API int sangnom_cuda_get_limits(int device, sn_limits* out);
+SN_API int sangnom_cuda_get_stats(sn_ctx* ctx, sn_stats* out);
+SN_API void sangnom_cuda_reset_stats(sn_ctx* ctx);
+
+/* Pinned host memory helpers for callers that want the zero-staging path. */
+SN_API void* sangnom_cuda_host_alloc(size_t bytes);
+SN_API void sangnom_cuda_host_free(void* p);
+
+/* Last error text of ctx (or of the calling thread's last failed create when ctx == NULL). */
+SN_API const char* sangnom_cuda_last_error(sn_ctx* ctx);
+SN_API int sangnom_cuda_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SANGNOM_CUDA_H */
