@@ -237,9 +237,11 @@ sn::PlaneTask make_task(const sn_ctx* ctx, const Pass& p, void* plane, size_t pi
     t.width = p.W; t.height = p.H; t.offset = p.job->offset;
     t.kept_rows = p.n; t.sweep_rows = p.R;
     t.thr_f = p.job->threshold;
-    // `const T aaf` (reference SangNom2.cpp:162,272): float -> T truncation for integer samples
-    if (ctx->sample_bytes == 1) t.thr_i = (int)(uint8_t)p.job->threshold;
-    else if (ctx->sample_bytes == 2) t.thr_i = (int)(uint16_t)p.job->threshold;
+    // `const T aaf` (reference SangNom2.cpp:162,272): float -> T for integer samples. Truncate
+    // toward zero, then wrap to the container width - what x86-64 does for the (undefined in C++)
+    // negative case the legacy SangNom() entry can produce.
+    if (ctx->sample_bytes == 1) t.thr_i = (int)p.job->threshold & 0xFF;
+    else if (ctx->sample_bytes == 2) t.thr_i = (int)p.job->threshold & 0xFFFF;
     t.in = p.in; t.out = p.out;
     return t;
 }

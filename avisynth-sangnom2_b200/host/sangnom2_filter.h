@@ -1,0 +1,48 @@
+// AviSynth filter class of the B200 SangNom2 plugin.
+//
+// Keeps the reference's constructor signature and script surface
+// (/root/reference/src/SangNom2.h:40-67, SangNom2.cpp:275-330) but owns no scratch pool and no
+// CPU kernels: GetFrame is a thin host layer that batches frames into libsangnom_cuda
+// (include/sangnom_cuda.h). Uses only AviSynth+ API that exists with the same meaning in the real
+// avisynth.h, so it builds against the SDK header as well as against host/avs_stub/avisynth.h.
+#pragma once
+
+#include <map>
+#include <mutex>
+
+#include "avisynth.h"
+#include "sangnom_cuda.h"
+
+class SangNom2 : public GenericVideoFilter {
+    int order_;
+    bool dh_;
+    float aaf_[3];            // per-plane threshold in sample units, untruncated (reference :280-282)
+    bool process_plane_[3];
+    bool has_at_least_v8_;
+    int sample_bytes_;
+    int plane_count_;         // min(NumComponents, 3): planes the reference touches (:347)
+    bool has_alpha_;
+
+    sn_ctx* ctx_ = nullptr;
+    int batch_frames_;        // frames fetched and processed per cache miss on sequential access
+    int last_request_ = -2;
+    std::map<int, PVideoFrame> ready_;   // finished frames not yet (or recently) served
+    std::mutex mu_;
+
+    int field_offset(int n);
+    void process_batch(int first, int count, IScriptEnvironment* env);
+
+public:
+    SangNom2(PClip _child, int order, int aa, int aac, int threads, bool dh, bool luma, bool chroma, int opt, IScriptEnvironment* env);
+    ~SangNom2() override;
+    PVideoFrame __stdcall GetFrame(int n, IScriptEnvironment* env) override;
+    // One instance serves all host threads: GetFrame serialises on an internal lock and the
+    // device work is batched, so cloning one GPU context per thread (MT_MULTI_INSTANCE, what the
+    // reference answers at SangNom2.h:63-66 because of its per-instance scratch pool) would only
+    // multiply device memory.
+    int __stdcall SetCacheHints(int cachehints, int frame_range) override
+    {
+        (void)frame_range;
+        return cachehints == CACHE_GET_MTMODE ? MT_NICE_FILTER : 0;
+    }
+};

@@ -1,0 +1,221 @@
+// AviSynth plugin shim: SangNom2(...) and legacy SangNom(...) on libsangnom_cuda.
+//
+// Mirrors the script surface of /root/reference/src/SangNom2.cpp:
+//   AvisynthPluginInit3 + the two AddFunction signatures            :474-484
+//   Create_SangNom2 / Create_SangNom: defaults, checks, messages    :399-472
+//   ctor: threshold scaling, dh doubles vi.height                   :275-288
+//   GetFrame: field offset by order/parity, plane loop              :332-397
+// The per-plane compute (prepare / blur / finalize, :74-273) is NOT here: it runs on the GPU
+// behind sangnom_cuda_process_planes. There is no CPU fallback; if the device library cannot
+// create a context the filter constructor raises a script error.
+#include "sangnom2_filter.h"
+
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+namespace {
+
+int env_int(const char* name, int def, int lo, int hi)
+{
+    const char* v = std::getenv(name);
+    if (!v || !*v) return def;
+    const int x = std::atoi(v);
+    return x < lo ? lo : (x > hi ? hi : x);
+}
+
+const int kPlaneIds[3] = { PLANAR_Y, PLANAR_U, PLANAR_V };
+
+}  // namespace
+
+SangNom2::SangNom2(PClip _child, int order, int aa, int aac, int threads, bool dh, bool luma, bool chroma, int opt, IScriptEnvironment* env)
+    : GenericVideoFilter(_child), order_(order), dh_(dh), aaf_{ 0.0f, 0.0f, 0.0f }, process_plane_{ luma, chroma, chroma }
+{
+    (void)threads;   // dummy parameter, as in the reference (README.md:40-41)
+    (void)opt;       // validated by the factory; selects nothing here - there is one code path
+    has_at_least_v8_ = env->FunctionExists("propShow");
+    sample_bytes_ = vi.ComponentSize();
+    plane_count_ = vi.NumComponents() < 3 ? vi.NumComponents() : 3;
+    has_alpha_ = vi.NumComponents() == 4;
+
+    const int strength[3] = { aa, aac, aac };
+    for (int i = 0; i < plane_count_; ++i)
+        aaf_[i] = sangnom_cuda_threshold(strength[i], vi.BitsPerComponent(), sample_bytes_);
+
+    if (dh_) vi.height *= 2;
+
+    sn_config cfg{};
+    cfg.abi_version = SANGNOM_CUDA_ABI_VERSION;
+    cfg.device = env_int("SANGNOM_B200_DEVICE", 0, 0, 1023);
+    cfg.sample_type = sample_bytes_;
+    cfg.pool_width = vi.width;       // pool geometry comes from the OUTPUT luma size (:287-288)
+    cfg.pool_height = vi.height;
+    batch_frames_ = env_int("SANGNOM_B200_BATCH", 8, 1, 256);
+    cfg.max_frames_in_flight = batch_frames_ < 3 ? 3 : batch_frames_;
+    if (sangnom_cuda_create(&cfg, &ctx_) != SN_OK)
+        env->ThrowError("SangNom2: %s", sangnom_cuda_last_error(nullptr));
+}
+
+SangNom2::~SangNom2()
+{
+    ready_.clear();
+    sangnom_cuda_destroy(ctx_);
+}
+
+// 0 keeps the top field (rows 0,2,..), 1 the bottom field (reference :336-341).
+int SangNom2::field_offset(int n)
+{
+    switch (order_) {
+        case 0: return child->GetParity(n) ? 0 : 1;
+        case 1: return 0;
+        default: return 1;
+    }
+}
+
+void SangNom2::process_batch(int first, int count, IScriptEnvironment* env)
+{
+    std::vector<PVideoFrame> srcs((size_t)count), dsts((size_t)count);
+    std::vector<sn_plane_job> jobs;
+    jobs.reserve((size_t)count * 5);
+    for (int k = 0; k < count; ++k) {
+        const int n = first + k;
+        const int offset = field_offset(n);
+        srcs[k] = child->GetFrame(n, env);
+        dsts[k] = has_at_least_v8_ ? env->NewVideoFrameP(vi, &srcs[k]) : env->NewVideoFrame(vi);
+        for (int i = 0; i < plane_count_; ++i) {
+            const int plane = kPlaneIds[i];
+            sn_plane_job jb{};
+            jb.src = srcs[k]->GetReadPtr(plane);
+            jb.src_pitch = srcs[k]->GetPitch(plane);
+            jb.dst = dsts[k]->GetWritePtr(plane);
+            jb.dst_pitch = dsts[k]->GetPitch(plane);
+            jb.width = srcs[k]->GetRowSize(plane) / sample_bytes_;
+            jb.dst_height = dsts[k]->GetHeight(plane);
+            jb.offset = offset;
+            // dh forces every plane to be processed (:361-366); otherwise a disabled plane is copied (:369-374)
+            jb.mode = dh_ ? SN_MODE_DH : (process_plane_[i] ? SN_MODE_FIELD : SN_MODE_COPY);
+            jb.threshold = aaf_[i];
+            jb.plane = i;
+            jb.frame = n;
+            jobs.push_back(jb);
+        }
+        if (has_alpha_) {
+            // The reference leaves the alpha plane of the new frame unwritten (:346-348). We copy it;
+            // for dh every source row is written to both output rows of its pair.
+            const int reps = dh_ ? 2 : 1;
+            for (int r = 0; r < reps; ++r) {
+                sn_plane_job jb{};
+                jb.src = srcs[k]->GetReadPtr(PLANAR_A);
+                jb.src_pitch = srcs[k]->GetPitch(PLANAR_A);
+                jb.dst = dsts[k]->GetWritePtr(PLANAR_A) + (ptrdiff_t)r * dsts[k]->GetPitch(PLANAR_A);
+                jb.dst_pitch = (ptrdiff_t)dsts[k]->GetPitch(PLANAR_A) * reps;
+                jb.width = srcs[k]->GetRowSize(PLANAR_A) / sample_bytes_;
+                jb.dst_height = srcs[k]->GetHeight(PLANAR_A);
+                jb.mode = SN_MODE_COPY;
+                jb.plane = 3;
+                jb.frame = n;
+                jobs.push_back(jb);
+            }
+        }
+    }
+    if (sangnom_cuda_process_planes(ctx_, jobs.data(), (int)jobs.size()) != SN_OK)
+        env->ThrowError("SangNom2: %s", sangnom_cuda_last_error(ctx_));
+    for (int k = 0; k < count; ++k) ready_[first + k] = dsts[k];
+}
+
+PVideoFrame __stdcall SangNom2::GetFrame(int n, IScriptEnvironment* env)
+{
+    std::lock_guard<std::mutex> lk(mu_);
+    auto hit = ready_.find(n);
+    if (hit == ready_.end()) {
+        // Sequential pulls (the normal frameserver pattern) are served in batches so the GPU sees
+        // many planes per launch; a seek falls back to a single frame.
+        const bool sequential = (n == last_request_ + 1) || (n == 0 && last_request_ == -2);
+        int count = sequential ? batch_frames_ : 1;
+        const int last = vi.num_frames > 0 ? vi.num_frames - 1 : n;
+        if (n + count - 1 > last) count = last - n + 1;
+        if (count < 1) count = 1;
+        // frames already finished inside the window are not recomputed
+        for (int k = 1; k < count; ++k)
+            if (ready_.count(n + k)) { count = k; break; }
+        process_batch(n, count, env);
+        hit = ready_.find(n);
+    }
+    PVideoFrame out = hit->second;
+    last_request_ = n;
+    // keep a bounded window of finished frames around the read position
+    while ((int)ready_.size() > 2 * batch_frames_) {
+        auto lo = ready_.begin();
+        auto hi = std::prev(ready_.end());
+        if (lo->first != n && n - lo->first >= hi->first - n) ready_.erase(lo);
+        else if (hi->first != n) ready_.erase(hi);
+        else break;
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Factories. Checks run on the INPUT clip's VideoInfo, in the reference's order, with the
+// reference's messages (SangNom2.cpp:407-422 / :446-459), including the "-1..2" wording.
+namespace {
+
+void validate(const char* name, const VideoInfo& vi, int order, int aa, const int* aac, int opt, IScriptEnvironment* env)
+{
+    const std::string n(name);
+    if (vi.IsRGB() || !vi.IsPlanar()) env->ThrowError((n + ": clip must be in Y/YUV planar format.").c_str());
+    if (vi.height % 2 != 0) env->ThrowError((n + ": height must be even.").c_str());
+    if (vi.Is420() && vi.height % 4) env->ThrowError((n + ": height must be mod4.").c_str());
+    if (order < 0 || order > 2) env->ThrowError((n + ": order must be between 0..2.").c_str());
+    if (aa < 0 || aa > 128) env->ThrowError((n + ": aa must be between 0..128.").c_str());
+    if (aac && (*aac < 0 || *aac > 128)) env->ThrowError((n + ": aac must be between 0..128.").c_str());
+    if (opt < -1 || opt > 1) env->ThrowError((n + ": opt must be between -1..2.").c_str());
+    if (!(env->GetCPUFlags() & CPUF_SSE2) && opt == 1) env->ThrowError((n + ": opt=1 requires SSE2.").c_str());
+}
+
+AVSValue __cdecl Create_SangNom2(AVSValue args, void*, IScriptEnvironment* env)
+{
+    PClip clip = args[0].AsClip();
+    const VideoInfo& vi = clip->GetVideoInfo();
+    const int order = args[1].AsInt(1);
+    const int aa = args[2].AsInt(48);
+    const int aac = args[3].AsInt(0);
+    const int threads = args[4].AsInt(0);
+    const bool dh = args[5].AsBool(false);
+    const bool luma = args[6].AsBool(true);
+    const bool chroma = args[7].AsBool(true);
+    const int opt = args[8].AsInt(-1);
+    validate("SangNom2", vi, order, aa, &aac, opt, env);
+    return new SangNom2(clip, order, aa, aac, threads, dh, luma, chroma, opt, env);
+}
+
+// Legacy SangNom(clip, order, aa, opt): order is remapped {0->2, 1->1, 2->0} (:441,463).
+// The reference's body reads the 4-entry argument array with SangNom2's indices (:443-444,
+// :466-470). Observable result, reproduced here: the value the script passes as `opt` lands in
+// aac (default 0 when omitted, never range-checked); threads/dh/luma/chroma/opt come from
+// out-of-range subscripts and so take their defaults (0, false, true, true, -1), which also means
+// the opt checks can never fire for this function.
+AVSValue __cdecl Create_SangNom(AVSValue args, void*, IScriptEnvironment* env)
+{
+    PClip clip = args[0].AsClip();
+    const VideoInfo& vi = clip->GetVideoInfo();
+    const int order = args[1].AsInt(1);
+    const int aa = args[2].AsInt(48);
+    const int aac_from_opt_slot = args[3].AsInt(0);   // the script's `opt`
+    const int opt = -1;
+    validate("SangNom", vi, order, aa, nullptr, opt, env);
+    static const int remap[3] = { 2, 1, 0 };
+    return new SangNom2(clip, remap[order], aa, aac_from_opt_slot, 0, false, true, true, opt, env);
+}
+
+}  // namespace
+
+const AVS_Linkage* AVS_linkage = nullptr;
+
+extern "C" __attribute__((visibility("default")))
+const char* __stdcall AvisynthPluginInit3(IScriptEnvironment* env, const AVS_Linkage* const vectors)
+{
+    AVS_linkage = vectors;
+    env->AddFunction("SangNom2", "c[order]i[aa]i[aac]i[threads]i[dh]b[luma]b[chroma]b[opt]i", Create_SangNom2, 0);
+    env->AddFunction("SangNom", "c[order]i[aa]i[opt]i", Create_SangNom, 0);
+    return "SangNom2";
+}

@@ -1,0 +1,140 @@
+"""Plugin-level parity on the GPU: our AviSynth plugin, driven by the fake host exactly like the
+reference plugin, against the oracle / golden fixtures / (when built) the live reference."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import CASES, assert_planes_equal, case_frames, oracle_outputs, parity_of
+from kat import KAT_IN, KATS
+from oracle import oracle as O
+from pysangnom.clips import make_frame
+from pysangnom.fakehost import FORMATS, MT_NICE_FILTER, FakeHost
+
+pytestmark = pytest.mark.gpu
+PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "avisynth-sangnom2_b200")
+OURS = os.path.join(PKG, "libsangnom2_b200.so")
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def run_plugin(plugin, fmt, w, h, frames, kw, func="SangNom2", fresh=False, **host_kw):
+    outs = []
+    with FakeHost(**host_kw) as host:
+        host.load_plugin(plugin)
+        src = host.source(w, h, fmt, len(frames), parity_mode=2)
+        for i, fr in enumerate(frames):
+            src.set_frame(i, fr)
+        flt = None
+        for i in range(len(frames)):
+            if flt is None or fresh:
+                flt = host.invoke(func, src, **kw)
+            outs.append(flt.get_frame(i))
+    return outs
+
+
+@pytest.mark.parametrize("kw,expected", KATS, ids=["order1_aa48", "order2_aa48", "order1_aa0"])
+def test_known_answers(kw, expected):
+    out = run_plugin(OURS, FORMATS["Y8"], 16, 8, [[KAT_IN]], kw)
+    assert np.array_equal(out[0][0], expected)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_plugin_matches_golden_and_oracle(case):
+    name, fmtname, w, h, kw, kind, nframes = case
+    fmt, frames = case_frames(case)
+    got = run_plugin(OURS, fmt, w, h, frames, kw)      # ONE long-lived instance, batched internally
+    g = GOLDEN["cases"][name]
+    assert [[sha(p) for p in fr[:3]] for fr in got] == g["output_sha256"], "differs from the reference-generated fixture"
+    exp = oracle_outputs(fmt, frames, kw)
+    for i in range(nframes):
+        assert_planes_equal(got[i][:3], exp[i][:3], f"{name} frame {i}")
+
+
+@pytest.mark.skipif(O.reference_plugin_path() is None, reason="oracle/_ref not built")
+@pytest.mark.parametrize("func,kw", [("SangNom2", dict(order=0, aa=30, aac=70)), ("SangNom", dict(order=0, aa=48)),
+                                     ("SangNom", dict(order=2, aa=48, opt=1)), ("SangNom", dict(order=1, aa=10, opt=0))])
+@pytest.mark.parametrize("fmtname", ["YV12", "YUV420P16", "YUV420PS"])
+def test_same_calls_on_both_plugins(func, kw, fmtname):
+    """Identical host call sequence on the reference plugin (C++ path: host reports no SSE2) and on ours.
+    Covers the legacy SangNom() entry: order remap and its aac := opt quirk (SangNom2.cpp:437-472)."""
+    fmt = FORMATS[fmtname]
+    w, h = 176, 144
+    frames = [make_frame(21, w, h, fmt, "edges", i) for i in range(3)]
+    ref = run_plugin(O.reference_plugin_path(), fmt, w, h, frames, kw, func=func, fresh=True, cpu_flags=0)
+    got = run_plugin(OURS, fmt, w, h, frames, kw, func=func, cpu_flags=0)
+    for i in range(3):
+        assert_planes_equal(got[i][:3], ref[i][:3], f"{func} {kw} {fmtname} frame {i}")
+
+
+def test_legacy_semantics_without_reference():
+    """SangNom(order=0) keeps the bottom field, (order=2) is double-rate; aac takes the script's opt."""
+    fmt = FORMATS["YV12"]
+    w, h = 96, 64
+    frames = [make_frame(4, w, h, fmt, "noise", i) for i in range(2)]
+    got = run_plugin(OURS, fmt, w, h, frames, dict(order=0, aa=48, opt=1), func="SangNom")
+    for i, fr in enumerate(frames):
+        exp = O.oracle_frame(fr, 8, order=2, aa=48, aac=1)
+        assert_planes_equal(got[i][:3], exp[:3], f"legacy frame {i}")
+    got = run_plugin(OURS, fmt, w, h, frames, dict(order=2), func="SangNom")
+    for i, fr in enumerate(frames):
+        exp = O.oracle_frame(fr, 8, order=0, aa=48, aac=0, parity=parity_of(i))
+        assert_planes_equal(got[i][:3], exp[:3], f"legacy dfr frame {i}")
+
+
+def test_filter_object_properties():
+    fmt = FORMATS["YUVA420P8"]
+    w, h, n = 64, 32, 5
+    with FakeHost() as host:
+        host.load_plugin(OURS)
+        src = host.source(w, h, fmt, n)
+        frames = [make_frame(2, w, h, fmt, "noise", i) for i in range(n)]
+        for i, fr in enumerate(frames):
+            src.set_frame(i, fr)
+            src.set_prop(i, "_FieldBased", i)
+        flt = host.invoke("SangNom2", src, dh=True, aa=20)
+        info = flt.info()
+        assert (info["width"], info["height"], info["num_frames"]) == (w, 2 * h, n)      # dh doubles vi.height
+        assert flt.mt_mode() == MT_NICE_FILTER
+        planes, props = flt.get_frame(3, with_props=["_FieldBased"])
+        assert props == {"_FieldBased": 3}                                                 # NewVideoFrameP copies props
+        exp = O.oracle_frame(frames[3], 8, order=1, aa=20, dh=True)
+        assert_planes_equal(planes[:3], exp[:3], "dh frame 3")
+        assert np.array_equal(planes[3], np.repeat(frames[3][3], 2, axis=0))              # alpha: copied (row-doubled)
+    with FakeHost(has_v8=False) as host:
+        host.load_plugin(OURS)
+        src = host.source(w, h, fmt, 1)
+        src.set_frame(0, frames[0])
+        src.set_prop(0, "_FieldBased", 7)
+        planes, props = host.invoke("SangNom2", src).get_frame(0, with_props=["_FieldBased"])
+        assert props == {}                                                                 # pre-v8 host: NewVideoFrame
+
+
+def test_batched_prefetch_and_seek(monkeypatch):
+    monkeypatch.setenv("SANGNOM_B200_BATCH", "4")
+    fmt = FORMATS["Y8"]
+    w, h, n = 64, 32, 10
+    frames = [make_frame(6, w, h, fmt, "edges", i) for i in range(n)]
+    exp = [O.oracle_frame(fr, 8, order=0, parity=parity_of(i))[0] for i, fr in enumerate(frames)]
+    with FakeHost() as host:
+        host.load_plugin(OURS)
+        src = host.source(w, h, fmt, n, parity_mode=2)
+        for i, fr in enumerate(frames):
+            src.set_frame(i, fr)
+        flt = host.invoke("SangNom2", src, order=0)
+        assert np.array_equal(flt.get_frame(0)[0], exp[0])
+        assert src.requests() == [0, 1, 2, 3]              # first sequential miss pulls a whole batch
+        for i in (1, 2, 3):
+            assert np.array_equal(flt.get_frame(i)[0], exp[i])
+        assert src.requests() == [0, 1, 2, 3]              # served from the finished batch
+        assert np.array_equal(flt.get_frame(4)[0], exp[4])
+        assert src.requests()[4:] == [4, 5, 6, 7]
+        assert np.array_equal(flt.get_frame(9)[0], exp[9])   # seek: single frame, clip end respected
+        assert src.requests()[8:] == [9]
+        assert np.array_equal(flt.get_frame(8)[0], exp[8])   # backwards
+        assert np.array_equal(flt.get_frame(2)[0], exp[2])
