@@ -7,6 +7,7 @@
 // There is no CPU compute path in this file: without a CUDA device every call fails.
 #include "sangnom_cuda.h"
 #include "sangnom_kernels.h"
+#include "sangnom_plan.h"
 
 #include <algorithm>
 #include <cstdarg>
@@ -16,6 +17,7 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <chrono>
 
 namespace {
 
@@ -140,14 +142,8 @@ bool is_pinned_host(const void* p)
     return a.type == cudaMemoryTypeHost;
 }
 
-// Group jobs into frames, validate, and derive for every processed plane how many pool rows its
-// pass must sweep and which blurred cost cells it has to hand to the next pass.
-//
-// Reference behaviour being reproduced: every plane's cost recursion runs over the whole pool
-// (rows 1..Hb-1, all S columns; SangNom2.cpp:133-136,269-270) while only rows 1..n-1, cols < W are
-// freshly written for that plane (:79-81). So pass q reads, outside its own rectangle, what pass
-// q-1 left there - itself the result of q-1's recursion over what q-2 left, and so on. A cell
-// pass q reads at pool row r must therefore have been swept by every earlier pass of the frame.
+// Group jobs into frames and validate them; sangnom_plan.h derives for every processed plane how many
+// pool rows its pass must sweep and which blurred cost cells it hands to the next pass.
 int plan_frames(sn_ctx* ctx, const sn_plane_job* jobs, int njobs, bool device_entry, std::vector<FramePlan>& frames)
 {
     const int sb = ctx->sample_bytes;
@@ -183,50 +179,20 @@ int plan_frames(sn_ctx* ctx, const sn_plane_job* jobs, int njobs, bool device_en
             if (q.job->plane == jb.plane) return ctx->fail(SN_ERR_INVALID, "frame %d: plane %d given twice", jb.frame, jb.plane);
         f.passes.push_back(p);
     }
-    const int S = ctx->S, Hb = ctx->Hb;
     for (FramePlan& f : frames) {
         std::stable_sort(f.passes.begin(), f.passes.end(), [](const Pass& a, const Pass& b) { return a.job->plane < b.job->plane; });
         const int m = (int)f.passes.size();
-        for (int q = m - 1; q >= 0; --q) {
-            Pass& p = f.passes[q];
-            p.R = std::min(p.n - 1, Hb - 1);
-            if (q + 1 < m) p.R = std::max(p.R, std::min(Hb - 1, f.passes[q + 1].R + 1));
-        }
-        // cost state handed from pass q to pass q+1
-        size_t off = 0;
-        for (int q = 0; q + 1 < m; ++q) {
-            Pass& p = f.passes[q];
-            const Pass& nx = f.passes[q + 1];
-            sn::CostState st{};
-            // region A: rows inside the next pass's row range, columns right of its rectangle
-            const int a_rows = std::min(nx.n - 1, p.R);
-            if (nx.W < S && a_rows >= 1) {
-                st.a_x0 = nx.W; st.a_rows = a_rows;
-                st.a = reinterpret_cast<void*>(off + 1);   // offset+1 for now (0 means empty); fixed up at placement
-                off += align_up((size_t)sn::kNumCost * (a_rows + 1) * (S - nx.W) * sb, 256);
-            }
-            // region B: rows below the next pass's rectangle that its recursion still reads
-            const int b0 = std::max(nx.n, 1), b1 = std::min(std::min(nx.R + 1, Hb - 1), p.R);
-            if (b1 >= b0) {
-                st.b_r0 = b0; st.b_r1 = b1;
-                st.b = reinterpret_cast<void*>(off + 1);
-                off += align_up((size_t)sn::kNumCost * (b1 - b0 + 1) * S * sb, 256);
-            }
-            p.out = st;
-            f.passes[q + 1].in = st;
-        }
-        f.state_bytes = off;
+        sn::PassGeometry geo[3];
+        for (int q = 0; q < m; ++q) { geo[q] = sn::PassGeometry{}; geo[q].width = f.passes[q].W; geo[q].kept_rows = f.passes[q].n; }
+        f.state_bytes = sn::plan_frame_passes(geo, m, ctx->S, ctx->Hb, sb);
+        for (int q = 0; q < m; ++q) { f.passes[q].R = geo[q].sweep_rows; f.passes[q].in = geo[q].in; f.passes[q].out = geo[q].out; }
     }
     return SN_OK;
 }
 
 void place_state(FramePlan& f, char* base)
 {
-    auto fix = [&](sn::CostState& s) {
-        if (s.a) s.a = base + (reinterpret_cast<size_t>(s.a) - 1);
-        if (s.b) s.b = base + (reinterpret_cast<size_t>(s.b) - 1);
-    };
-    for (Pass& p : f.passes) { fix(p.in); fix(p.out); }
+    for (Pass& p : f.passes) { sn::plan_place_state(p.in, base); sn::plan_place_state(p.out, base); }
 }
 
 sn::PlaneTask make_task(const sn_ctx* ctx, const Pass& p, void* plane, size_t pitch_bytes)
@@ -452,12 +418,17 @@ int sangnom_cuda_process_planes_device(sn_ctx* ctx, const sn_plane_job* jobs, in
     if (njobs == 0) return SN_OK;
     std::lock_guard<std::mutex> lk(ctx->mu);
     SN_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
-    cudaStream_t stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_compute;
+    cudaStream_t stream = cuda_stream == SN_STREAM_CONTEXT ? ctx->own_compute : static_cast<cudaStream_t>(cuda_stream);
     const int sb = ctx->sample_bytes;
 
+    static const bool trace = getenv("SANGNOM_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
+    const auto t0 = now();
     std::vector<FramePlan> frames;
     int rc = plan_frames(ctx, jobs, njobs, true, frames);
     if (rc != SN_OK) return rc;
+    const auto t1 = now();
 
     size_t state_total = 0, ntasks = 0;
     for (FramePlan& f : frames) { f.state_off = state_total; state_total += align_up(f.state_bytes, 256); ntasks += f.passes.size(); }
@@ -487,24 +458,37 @@ int sangnom_cuda_process_planes_device(sn_ctx* ctx, const sn_plane_job* jobs, in
         }
     }
 
+    const auto t2 = now();
     std::vector<std::vector<sn::PlaneTask>> by_pass(3);
     for (FramePlan& f : frames)
         for (size_t q = 0; q < f.passes.size(); ++q)
             by_pass[q].push_back(make_task(ctx, f.passes[q], f.passes[q].job->dst, (size_t)f.passes[q].job->dst_pitch));
+    const auto t3 = now();
 
+    // Task arrays travel through a small ring of pinned/device buffers; all entries are grown
+    // together (one stream sync, first call only) so steady-state submission never blocks.
+    const size_t task_bytes = ntasks * sizeof(sn::PlaneTask);
+    if (task_bytes > ctx->dev_tasks[0].bytes) {
+        SN_CUDA(ctx, cudaStreamSynchronize(stream));
+        for (int i = 0; i < kTaskRing; ++i) {
+            SN_CUDA(ctx, cudaEventSynchronize(ctx->dev_task_free[i]));
+            SN_CUDA(ctx, ctx->dev_tasks_host[i].ensure(task_bytes));
+            SN_CUDA(ctx, ctx->dev_tasks[i].ensure(task_bytes));
+        }
+    }
     const int slot = ctx->dev_ring_pos;
     ctx->dev_ring_pos = (ctx->dev_ring_pos + 1) % kTaskRing;
     SN_CUDA(ctx, cudaEventSynchronize(ctx->dev_task_free[slot]));     // ring entry no longer read by an earlier upload
-    SN_CUDA(ctx, ctx->dev_tasks_host[slot].ensure(ntasks * sizeof(sn::PlaneTask)));
-    if (ntasks * sizeof(sn::PlaneTask) > ctx->dev_tasks[slot].bytes) {
-        SN_CUDA(ctx, cudaStreamSynchronize(stream));
-        SN_CUDA(ctx, ctx->dev_tasks[slot].ensure(ntasks * sizeof(sn::PlaneTask)));
-    }
     rc = launch_passes(ctx, by_pass, static_cast<sn::PlaneTask*>(ctx->dev_tasks_host[slot].p),
                        static_cast<sn::PlaneTask*>(ctx->dev_tasks[slot].p), stream);
     if (rc != SN_OK) return rc;
     SN_CUDA(ctx, cudaEventRecord(ctx->dev_task_free[slot], stream));
     ctx->stats.frames += frames.size();
+    if (trace) {
+        const auto t4 = now();
+        fprintf(stderr, "[sangnom] device submit: plan %ld us, place %ld us, tasks %ld us, ring+launch %ld us (%d jobs)\n",
+                us(t0, t1), us(t1, t2), us(t2, t3), us(t3, t4), njobs);
+    }
     return SN_OK;
 }
 

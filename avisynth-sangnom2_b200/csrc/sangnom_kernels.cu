@@ -18,8 +18,10 @@
 // recursion (SURVEY.md finding 2). That state is passed explicitly between passes as CostState
 // (sangnom_kernels.h) and every pass runs over the full pool width S, so the result is exact.
 #include "sangnom_kernels.h"
+#include "sangnom_u8.cuh"
 
 #include <cstdint>
+#include <cstdlib>
 
 namespace sn {
 
@@ -355,6 +357,23 @@ cudaError_t launch_variant(const PlaneTask* tasks, int ntasks, LaunchGeometry g,
     return cudaGetLastError();
 }
 
+template <int kMaxThreads, int kMinBlocks>
+cudaError_t launch_u8(const PlaneTask* tasks, int ntasks, LaunchGeometry g, cudaStream_t stream)
+{
+    const size_t smem = u8k::smem_bytes(g.S);
+    static size_t configured[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || smem > configured[dev]) {
+        e = cudaFuncSetAttribute(u8k::sangnom_u8_row_sweep<kMaxThreads, kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev] = smem;
+    }
+    u8k::sangnom_u8_row_sweep<kMaxThreads, kMinBlocks><<<ntasks, g.S / u8k::kCols, smem, stream>>>(tasks, g);
+    return cudaGetLastError();
+}
+
 template <typename T>
 cudaError_t launch_typed(const PlaneTask* tasks, int ntasks, LaunchGeometry g, cudaStream_t stream)
 {
@@ -374,7 +393,7 @@ const char* kernel_variant_name(int sample_bytes, int S)
 {
     const bool wide = S > 4 * kMaxThreads;
     switch (sample_bytes) {
-        case 1: return wide ? "sangnom_row_sweep<u8,8>" : "sangnom_row_sweep<u8,4>";
+        case 1: return S <= 2048 ? "sangnom_u8_row_sweep<256,3>" : "sangnom_u8_row_sweep<512,1>";
         case 2: return wide ? "sangnom_row_sweep<u16,8>" : "sangnom_row_sweep<u16,4>";
         default: return wide ? "sangnom_row_sweep<f32,8>" : "sangnom_row_sweep<f32,4>";
     }
@@ -385,7 +404,15 @@ cudaError_t launch_plane_tasks(int sample_bytes, const PlaneTask* tasks_dev, int
     if (ntasks <= 0) return cudaSuccess;
     if (g.S % 32 != 0 || g.S > max_pool_width(sample_bytes)) return cudaErrorInvalidValue;
     switch (sample_bytes) {
-        case 1: return launch_typed<uint8_t>(tasks_dev, ntasks, g, stream);
+        case 1: {
+            static const int occ = [] { const char* v = getenv("SANGNOM_U8_OCC"); return v ? atoi(v) : 2; }();   // tuning knob
+            if (occ == 0) return launch_typed<uint8_t>(tasks_dev, ntasks, g, stream);                           // generic kernel
+            if (g.S <= 256 * u8k::kCols) {
+                if (occ >= 3) return launch_u8<256, 3>(tasks_dev, ntasks, g, stream);
+                return launch_u8<256, 2>(tasks_dev, ntasks, g, stream);
+            }
+            return launch_u8<512, 1>(tasks_dev, ntasks, g, stream);
+        }
         case 2: return launch_typed<uint16_t>(tasks_dev, ntasks, g, stream);
         case 4: return launch_typed<float>(tasks_dev, ntasks, g, stream);
         default: return cudaErrorInvalidValue;

@@ -1,6 +1,8 @@
 // Internal interface between the C-ABI layer (sangnom_api.cu) and the kernels (sangnom_kernels.cu).
 #pragma once
+#ifndef SN_HOST_EMULATION
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace sn {

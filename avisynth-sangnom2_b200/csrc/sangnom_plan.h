@@ -1,0 +1,77 @@
+// Per-frame pass planning: pure host C++ (no CUDA), shared by the C-ABI layer and the kernel
+// emulation tests.
+//
+// Reference behaviour being reproduced: every plane's cost recursion runs over the whole scratch
+// pool (rows 1..Hb-1, all S columns; /root/reference/src/SangNom2.cpp:133-136,269-270) while only
+// rows 1..n-1, columns < W are freshly written for that plane (:79-81), and the pool is shared by
+// the planes of a frame and never cleared (:303-310). So pass q reads, outside its own rectangle,
+// what pass q-1 left there - itself the result of q-1's recursion over what q-2 left, and so on.
+// Consequences planned here:
+//   * a cell pass q reads at pool row r must have been swept by every earlier pass of the frame,
+//     so earlier passes may have to sweep more rows than their own picture needs (sweep_rows);
+//   * pass q hands pass q+1 exactly the cells q+1 will read outside its rectangle (CostState).
+#pragma once
+#include <algorithm>
+#include <cstddef>
+#include <cstdint>
+
+#include "sangnom_kernels.h"
+
+namespace sn {
+
+struct PassGeometry {
+    int width;        // W: picture columns of this plane
+    int kept_rows;    // n = H/2
+    int sweep_rows;   // out: R
+    CostState in, out;   // out: regions; pointers hold (byte offset + 1) into the frame's state scratch, 0 = empty
+};
+
+inline size_t plan_align(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// passes[0..m) in processing order (Y,U,V). Returns the bytes of cost-state scratch the frame needs.
+inline size_t plan_frame_passes(PassGeometry* passes, int m, int S, int Hb, int sample_bytes)
+{
+    for (int q = m - 1; q >= 0; --q) {
+        PassGeometry& p = passes[q];
+        p.in = CostState{};
+        p.out = CostState{};
+        p.sweep_rows = std::min(p.kept_rows - 1, Hb - 1);
+        if (q + 1 < m) p.sweep_rows = std::max(p.sweep_rows, std::min(Hb - 1, passes[q + 1].sweep_rows + 1));
+    }
+    size_t off = 0;
+    for (int q = 0; q + 1 < m; ++q) {
+        PassGeometry& p = passes[q];
+        const PassGeometry& nx = passes[q + 1];
+        CostState st{};
+        // region A: rows inside the next pass's row range, columns right of its rectangle. Stored from
+        // the 8-column boundary at or left of the next pass's width so that a thread's column group is
+        // one aligned vector; the reader masks by its own width.
+        const int a_rows = std::min(nx.kept_rows - 1, p.sweep_rows);
+        if (nx.width < S && a_rows >= 1) {
+            st.a_x0 = nx.width & ~7;
+            st.a_rows = a_rows;
+            st.a = reinterpret_cast<void*>(off + 1);
+            off += plan_align((size_t)kNumCost * (a_rows + 1) * (S - st.a_x0) * sample_bytes, 256);
+        }
+        // region B: rows below the next pass's rectangle that its recursion still reads (row Hb and
+        // beyond are never written by anyone: they read as the pool's initial zero)
+        const int b0 = std::max(nx.kept_rows, 1), b1 = std::min(std::min(nx.sweep_rows + 1, Hb - 1), p.sweep_rows);
+        if (b1 >= b0) {
+            st.b_r0 = b0;
+            st.b_r1 = b1;
+            st.b = reinterpret_cast<void*>(off + 1);
+            off += plan_align((size_t)kNumCost * (b1 - b0 + 1) * S * sample_bytes, 256);
+        }
+        p.out = st;
+        passes[q + 1].in = st;
+    }
+    return off;
+}
+
+inline void plan_place_state(CostState& s, char* base)
+{
+    if (s.a) s.a = base + (reinterpret_cast<size_t>(s.a) - 1);
+    if (s.b) s.b = base + (reinterpret_cast<size_t>(s.b) - 1);
+}
+
+}  // namespace sn

@@ -177,8 +177,10 @@ class Context:
         self._check(load().sangnom_cuda_process_planes(self._h, arr, len(jobs)))
 
     def process_jobs_device(self, jobs, stream=None):
+        """stream: a cudaStream_t handle as int (0 = CUDA's legacy default stream); None = the context's own stream."""
         arr = jobs if isinstance(jobs, C.Array) else (SnPlaneJob * len(jobs))(*jobs)
-        self._check(load().sangnom_cuda_process_planes_device(self._h, arr, len(arr), C.c_void_p(stream or 0)))
+        handle = C.c_void_p(-1) if stream is None else C.c_void_p(stream)
+        self._check(load().sangnom_cuda_process_planes_device(self._h, arr, len(arr), handle))
 
     def synchronize(self):
         self._check(load().sangnom_cuda_synchronize(self._h))

@@ -121,9 +121,12 @@ SN_API void sangnom_cuda_destroy(sn_ctx* ctx);
  * pipelined internally (H2D | kernels | D2H on three streams). */
 SN_API int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs);
 
-/* DEVICE buffers: src/dst are device pointers on ctx's device. Asynchronous on `cuda_stream`
- * (a cudaStream_t passed as void*; NULL = the context's compute stream); no host/device copies.
- * The job list is consumed before the call returns. */
+/* DEVICE buffers: src/dst are device pointers on ctx's device. Asynchronous on `cuda_stream`, a
+ * cudaStream_t passed as void* (NULL is CUDA's legacy default stream, as everywhere in CUDA;
+ * SN_STREAM_CONTEXT selects the context's own compute stream); no host/device copies.
+ * The job list is consumed before the call returns. Calls on one context share its cost-state
+ * scratch, so they must be stream-ordered with respect to each other. */
+#define SN_STREAM_CONTEXT ((void*)(intptr_t)-1)
 SN_API int sangnom_cuda_process_planes_device(sn_ctx* ctx, const sn_plane_job* jobs, int njobs, void* cuda_stream);
 
 /* Block until everything queued by _device on the context's own stream has finished. */

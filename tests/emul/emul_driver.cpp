@@ -1,0 +1,46 @@
+// Runs the device kernels of csrc/*.cuh on the CPU through tests/emul/cuda_emul.h, one emulated
+// thread block per plane pass, with the same per-frame pass planning the C-ABI layer uses
+// (csrc/sangnom_plan.h). TEST INFRASTRUCTURE ONLY - see cuda_emul.h.
+#include "cuda_emul.h"
+
+#include "sangnom_plan.h"
+#include "sangnom_u8.cuh"
+
+#include <cstdio>
+
+extern "C" {
+
+// One frame: up to 3 processed planes, in place (kept field already in the dst planes).
+// planes[i]: pointer to row 0; pitch in BYTES; returns 0, or -1 for unsupported geometry.
+int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long long* pitch_bytes, const int* widths,
+               const int* heights, const int* offsets, const float* thresholds, int pool_width, int pool_height)
+{
+    const int S = (pool_width + 31) & ~31, Hb = (pool_height + 1) >> 1;
+    sn::PassGeometry geo[3];
+    for (int q = 0; q < nplanes; ++q) { geo[q] = sn::PassGeometry{}; geo[q].width = widths[q]; geo[q].kept_rows = heights[q] / 2; }
+    const size_t state_bytes = sn::plan_frame_passes(geo, nplanes, S, Hb, sample_bytes);
+    std::vector<char> state(state_bytes + 256, (char)0x5A);      // poisoned: a read of a never-written cell is visible
+    char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(state.data()) + 255) & ~(uintptr_t)255);
+    for (int q = 0; q < nplanes; ++q) {
+        sn::plan_place_state(geo[q].in, base);
+        sn::plan_place_state(geo[q].out, base);
+        sn::PlaneTask t{};
+        t.plane = planes[q];
+        t.pitch = pitch_bytes[q] / sample_bytes;
+        t.width = widths[q]; t.height = heights[q]; t.offset = offsets[q];
+        t.kept_rows = geo[q].kept_rows; t.sweep_rows = geo[q].sweep_rows;
+        t.thr_f = thresholds[q];
+        t.thr_i = sample_bytes == 1 ? ((int)thresholds[q] & 0xFF) : ((int)thresholds[q] & 0xFFFF);
+        t.in = geo[q].in; t.out = geo[q].out;
+        sn::LaunchGeometry g{ S, Hb };
+        if (sample_bytes == 1) {
+            const unsigned threads = (unsigned)(S / sn::u8k::kCols);
+            emul::run_block(0, threads, sn::u8k::smem_bytes(S), [&] { sn::u8k::sangnom_u8_row_sweep<1024, 1>(&t, g); });
+        } else {
+            return -1;
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"
