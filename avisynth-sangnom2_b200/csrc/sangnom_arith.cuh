@@ -1,0 +1,81 @@
+// Scalar pixel arithmetic of the reference's opt=0 path for the 16-bit and fp32 flavours
+// (/root/reference/src/SangNom2.cpp:36-72, :108-117, :208-249). Integer flavours compute in int32 and
+// wrap to the container width where the reference narrows to T; fp32 rounds every operation
+// separately in the reference's order (no FMA contraction anywhere: explicit __f*_rn).
+#pragma once
+#include "sangnom_kernels.h"
+
+#include <cstdint>
+
+namespace sn {
+
+template <typename T> struct Flavour;
+template <> struct Flavour<uint8_t>  { using I = int;   static constexpr bool kFloat = false; static constexpr int kMask = 0xFF; };
+template <> struct Flavour<uint16_t> { using I = int;   static constexpr bool kFloat = false; static constexpr int kMask = 0xFFFF; };
+template <> struct Flavour<float>    { using I = float; static constexpr bool kFloat = true;  static constexpr int kMask = -1; };
+
+// rank of cost buffer i in the reference's tie order: 4 first, then 5,3,6,2,7,1,8,0 (:214-249)
+__device__ __forceinline__ constexpr int rank_of(int i)
+{
+    constexpr int r[kNumCost] = { 8, 6, 4, 2, 0, 1, 3, 5, 7 };
+    return r[i];
+}
+
+template <typename T> __device__ __forceinline__ int tap3_int(int p1, int p2, int p3)
+{
+    return ((4 * p1 + 5 * p2 - p3) >> 3) & Flavour<T>::kMask;      // arithmetic shift, then wrap to T (:63-64)
+}
+__device__ __forceinline__ float tap3_f32(float p1, float p2, float p3)
+{
+    return __fmul_rn(__fsub_rn(__fadd_rn(__fmul_rn(p1, 4.0f), __fmul_rn(p2, 5.0f)), p3), 0.125f);   // (:70-71)
+}
+template <typename T, typename I> __device__ __forceinline__ I tap3(I p1, I p2, I p3)
+{
+    if constexpr (Flavour<T>::kFloat) return tap3_f32(p1, p2, p3);
+    else return tap3_int<T>(p1, p2, p3);
+}
+__device__ __forceinline__ int absdiff(int a, int b) { return abs(a - b); }
+__device__ __forceinline__ float absdiff(float a, float b) { return fabsf(__fsub_rn(a, b)); }
+__device__ __forceinline__ int mean2(int a, int b) { return (a + b + 1) >> 1; }
+__device__ __forceinline__ float mean2(float a, float b) { return __fmul_rn(__fadd_rn(a, b), 0.5f); }
+__device__ __forceinline__ int add2(int a, int b) { return a + b; }
+__device__ __forceinline__ float add2(float a, float b) { return __fadd_rn(a, b); }
+
+// The nine raw costs of pixel p. wc/wn: cur/next row windows, pixel p at index p + kHalo.
+template <typename T, typename I, int N, int kHalo>
+__device__ __forceinline__ void raw_costs(const I (&wc)[N], const I (&wn)[N], int p, I (&cost)[kNumCost])
+{
+    const int q = p + kHalo;
+    const I f1 = tap3<T, I>(wc[q - 1], wc[q], wc[q + 1]);
+    const I f2 = tap3<T, I>(wn[q + 1], wn[q], wn[q - 1]);
+    const I b1 = tap3<T, I>(wc[q + 1], wc[q], wc[q - 1]);
+    const I b2 = tap3<T, I>(wn[q - 1], wn[q], wn[q + 1]);
+    cost[0] = absdiff(wc[q - 3], wn[q + 3]);
+    cost[1] = absdiff(wc[q - 2], wn[q + 2]);
+    cost[2] = absdiff(wc[q - 1], wn[q + 1]);
+    cost[3] = absdiff(f1, f2);
+    cost[4] = absdiff(wc[q], wn[q]);
+    cost[5] = absdiff(b1, b2);
+    cost[6] = absdiff(wc[q + 1], wn[q - 1]);
+    cost[7] = absdiff(wc[q + 2], wn[q - 2]);
+    cost[8] = absdiff(wc[q + 3], wn[q - 3]);
+}
+
+// Interpolated value of pixel p from the winning rank (0 = plain vertical mean).
+template <typename T, typename I, int N, int kHalo>
+__device__ __forceinline__ I interpolate_rank(const I (&wc)[N], const I (&wn)[N], int p, int rank)
+{
+    const int q = p + kHalo;
+    I a = wc[q], b = wn[q];
+    if (rank == 1) { a = tap3<T, I>(wc[q + 1], wc[q], wc[q - 1]); b = tap3<T, I>(wn[q - 1], wn[q], wn[q + 1]); }
+    if (rank == 2) { a = tap3<T, I>(wc[q - 1], wc[q], wc[q + 1]); b = tap3<T, I>(wn[q + 1], wn[q], wn[q - 1]); }
+    if (rank == 3) { a = wc[q + 1]; b = wn[q - 1]; }
+    if (rank == 4) { a = wc[q - 1]; b = wn[q + 1]; }
+    if (rank == 5) { a = wc[q + 2]; b = wn[q - 2]; }
+    if (rank == 6) { a = wc[q - 2]; b = wn[q + 2]; }
+    if (rank == 7) { a = wc[q + 3]; b = wn[q - 3]; }
+    if (rank == 8) { a = wc[q - 3]; b = wn[q + 3]; }
+    return mean2(a, b);
+}
+
+}  // namespace sn

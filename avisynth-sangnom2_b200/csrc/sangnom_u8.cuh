@@ -12,6 +12,7 @@
 // Reference semantics: /root/reference/src/SangNom2.cpp :60-65 (3-tap), :108-117 (costs),
 // :138-152 (recursive blur, /16, wrap to u8), :208-249 (min, threshold, tie order, rounding mean).
 #pragma once
+#include "sangnom_cluster.cuh"
 #include "sangnom_kernels.h"
 
 #include <cstdint>
@@ -216,17 +217,23 @@ __device__ __forceinline__ uint2 interpolate8(const Taps& c, const Taps& n, cons
 
 template <int kMaxThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
-sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g)
+sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int seg_cols)
 {
     SN_DYNAMIC_SMEM(smem_raw);
-    const PlaneTask t = tasks[blockIdx.x];
+    // a plane wider than one block is split into column segments over the blocks of a cluster
+    const unsigned G = cl::size();
+    const unsigned crank = cl::rank();
+    const bool clustered = G > 1;
+    const PlaneTask t = tasks[blockIdx.x / G];
     const int S = g.S;
-    const int LS = S + 2 * kLPad;                                   // u16 elements per shared L row
+    const int LS = seg_cols + 2 * kLPad;                            // u16 elements per shared L row of this segment
     uint16_t* const Lbase = reinterpret_cast<uint16_t*>(smem_raw);  // [2][9][LS]
 
     const int W = t.width, n = t.kept_rows, R = t.sweep_rows;
-    const int x0 = threadIdx.x * kCols;
-    const bool first_thread = threadIdx.x == 0, last_thread = x0 + kCols == S;
+    const int lx = threadIdx.x * kCols;                             // column inside the segment
+    const int x0 = (int)crank * seg_cols + lx;                      // pool column
+    const bool plane_first = x0 == 0, plane_last = x0 + kCols == S;
+    const bool seg_first = lx == 0, seg_last = lx + kCols == seg_cols;
     uint8_t* const plane = static_cast<uint8_t*>(t.plane);
     const long long pitch = t.pitch;
     const bool vec = ((reinterpret_cast<uintptr_t>(plane) | (uintptr_t)pitch) & 15) == 0 && pitch >= (((long long)W + 15) & ~15LL);
@@ -310,19 +317,31 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g)
                 uint4 L;
                 L.x = M[i][0] + P[i][0]; L.y = M[i][1] + P[i][1]; L.z = M[i][2] + P[i][2]; L.w = M[i][3] + P[i][3];
                 uint16_t* row = Lrow + i * LS;
-                *reinterpret_cast<uint4*>(row + x0) = L;
-                if (first_thread) { const uint32_t e = (L.x & 0xFFFFu) * 0x00010001u; *reinterpret_cast<uint2*>(row - 4) = make_uint2(e, e); }
-                if (last_thread) { const uint32_t e = (L.w >> 16) * 0x00010001u; *reinterpret_cast<uint2*>(row + S) = make_uint2(e, e); }
+                *reinterpret_cast<uint4*>(row + lx) = L;
+                if (seg_first) {
+                    if (plane_first) { const uint32_t e = (L.x & 0xFFFFu) * 0x00010001u; *reinterpret_cast<uint2*>(row - 4) = make_uint2(e, e); }   // clamp at column 0
+                    else {                                                       // my first columns are the left neighbour's right halo
+                        cl::store_remote(reinterpret_cast<uint32_t*>(row + seg_cols), crank - 1, L.x);
+                        cl::store_remote(reinterpret_cast<uint32_t*>(row + seg_cols + 2), crank - 1, L.y);
+                    }
+                }
+                if (seg_last) {
+                    if (plane_last) { const uint32_t e = (L.w >> 16) * 0x00010001u; *reinterpret_cast<uint2*>(row + seg_cols) = make_uint2(e, e); }   // clamp at column S-1
+                    else {                                                       // my last columns are the right neighbour's left halo
+                        cl::store_remote(reinterpret_cast<uint32_t*>(row - 4), crank + 1, L.z);
+                        cl::store_remote(reinterpret_cast<uint32_t*>(row - 2), crank + 1, L.w);
+                    }
+                }
                 M[i][0] = P[i][0]; M[i][1] = P[i][1]; M[i][2] = P[i][2]; M[i][3] = P[i][3];
             }
         }
-        __syncthreads();
+        cl::row_barrier(clustered);
 
         // ---- B[r] = wrap8(H7(L) >> 4) per buffer; keys for the min; M += B ----
         uint32_t kmin[4] = { tkey, tkey, tkey, tkey };
 #pragma unroll
         for (int i = 0; i < kNumCost; ++i) {
-            const uint16_t* row = Lrow + i * LS + x0;
+            const uint16_t* row = Lrow + i * LS + lx;
             const uint2 lh = *reinterpret_cast<const uint2*>(row - 4);      // (l-4,l-3) (l-2,l-1)
             const uint4 own = *reinterpret_cast<const uint4*>(row);         // (l0,l1) .. (l6,l7)
             const uint2 rh = *reinterpret_cast<const uint2*>(row + 8);      // (l8,l9) (l10,l11)
@@ -361,7 +380,7 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g)
     }
 }
 
-inline size_t smem_bytes(int S) { return (size_t)2 * kNumCost * (S + 2 * kLPad) * sizeof(uint16_t); }
+inline size_t smem_bytes(int seg_cols) { return (size_t)2 * kNumCost * (seg_cols + 2 * kLPad) * sizeof(uint16_t); }
 
 }  // namespace u8k
 }  // namespace sn

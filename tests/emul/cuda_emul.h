@@ -6,9 +6,12 @@
 #pragma once
 #include <algorithm>
 #include <barrier>
+#include <math.h>
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -37,6 +40,10 @@ namespace emul {
 inline thread_local dim3e tidx, bidx, bdim;
 inline thread_local unsigned char* smem = nullptr;
 inline thread_local std::barrier<>* bar = nullptr;
+// thread block cluster: rank of this block, cluster size, every block's shared memory, cluster-wide barrier
+inline thread_local unsigned crank = 0, csize = 1;
+inline thread_local unsigned char* const* cluster_smem = nullptr;
+inline thread_local std::barrier<>* cluster_bar = nullptr;
 }  // namespace emul
 #define threadIdx (emul::tidx)
 #define blockIdx (emul::bidx)
@@ -78,6 +85,9 @@ inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 using std::max;
+
+
+using std::abs;
 using std::min;
 
 namespace emul {
@@ -95,6 +105,29 @@ void run_block(unsigned block, unsigned threads, size_t smem_bytes, F&& body)
             smem = sm; bar = &barrier;
             body();
         });
+    for (auto& th : pool) th.join();
+}
+
+// Run one cluster of `nblocks` blocks (block indices first_block..first_block+nblocks-1) concurrently.
+template <typename F>
+void run_cluster(unsigned first_block, unsigned nblocks, unsigned threads, size_t smem_bytes, F&& body)
+{
+    std::vector<std::vector<unsigned char>> shared(nblocks, std::vector<unsigned char>(smem_bytes + 64, 0xA5));
+    std::vector<unsigned char*> bases(nblocks);
+    for (unsigned b = 0; b < nblocks; ++b)
+        bases[b] = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(shared[b].data()) + 15) & ~(uintptr_t)15);
+    std::vector<std::unique_ptr<std::barrier<>>> block_bars;
+    for (unsigned b = 0; b < nblocks; ++b) block_bars.emplace_back(new std::barrier<>((std::ptrdiff_t)threads));
+    std::barrier<> cbar((std::ptrdiff_t)threads * nblocks);
+    std::vector<std::thread> pool;
+    for (unsigned b = 0; b < nblocks; ++b)
+        for (unsigned t = 0; t < threads; ++t)
+            pool.emplace_back([&, b, t] {
+                tidx = dim3e{ t, 0, 0 }; bidx = dim3e{ first_block + b, 0, 0 }; bdim = dim3e{ threads, 1, 1 };
+                smem = bases[b]; bar = block_bars[b].get();
+                crank = b; csize = nblocks; cluster_smem = bases.data(); cluster_bar = &cbar;
+                body();
+            });
     for (auto& th : pool) th.join();
 }
 }  // namespace emul

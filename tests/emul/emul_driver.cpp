@@ -5,6 +5,7 @@
 
 #include "sangnom_plan.h"
 #include "sangnom_u8.cuh"
+#include "sangnom_wide.cuh"
 
 #include <cstdio>
 
@@ -13,7 +14,7 @@ extern "C" {
 // One frame: up to 3 processed planes, in place (kept field already in the dst planes).
 // planes[i]: pointer to row 0; pitch in BYTES; returns 0, or -1 for unsupported geometry.
 int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long long* pitch_bytes, const int* widths,
-               const int* heights, const int* offsets, const float* thresholds, int pool_width, int pool_height)
+               const int* heights, const int* offsets, const float* thresholds, int pool_width, int pool_height, int cluster)
 {
     const int S = (pool_width + 31) & ~31, Hb = (pool_height + 1) >> 1;
     sn::PassGeometry geo[3];
@@ -33,12 +34,17 @@ int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long lo
         t.thr_i = sample_bytes == 1 ? ((int)thresholds[q] & 0xFF) : ((int)thresholds[q] & 0xFFFF);
         t.in = geo[q].in; t.out = geo[q].out;
         sn::LaunchGeometry g{ S, Hb };
-        if (sample_bytes == 1) {
-            const unsigned threads = (unsigned)(S / sn::u8k::kCols);
-            emul::run_block(0, threads, sn::u8k::smem_bytes(S), [&] { sn::u8k::sangnom_u8_row_sweep<1024, 1>(&t, g); });
-        } else {
-            return -1;
-        }
+        const unsigned G = (unsigned)cluster;
+        const int cols = sample_bytes == 1 ? sn::u8k::kCols : sn::wide::kCols;
+        if (S % (int)(G * cols) != 0) return -1;
+        const int seg = S / (int)G;
+        const unsigned threads = (unsigned)(seg / cols);
+        if (sample_bytes == 1)
+            emul::run_cluster(0, G, threads, sn::u8k::smem_bytes(seg), [&] { sn::u8k::sangnom_u8_row_sweep<1024, 1>(&t, g, seg); });
+        else if (sample_bytes == 2)
+            emul::run_cluster(0, G, threads, sn::wide::smem_bytes<uint16_t>(seg), [&] { sn::wide::sangnom_wide_row_sweep<uint16_t, 1024, 1>(&t, g, seg); });
+        else
+            emul::run_cluster(0, G, threads, sn::wide::smem_bytes<float>(seg), [&] { sn::wide::sangnom_wide_row_sweep<float, 1024, 1>(&t, g, seg); });
     }
     return 0;
 }

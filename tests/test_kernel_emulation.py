@@ -26,11 +26,11 @@ def emul():
     L = C.CDLL(EMUL)
     L.emul_frame.restype = C.c_int
     L.emul_frame.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.POINTER(C.c_int),
-                             C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int, C.c_int]
+                             C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int]
     return L
 
 
-def emulate(L, planes, bits, order=1, aa=48, aac=0, dh=False, luma=True, chroma=True, parity=True):
+def emulate(L, planes, bits, order=1, aa=48, aac=0, dh=False, luma=True, chroma=True, parity=True, cluster=1):
     """Frame-level host logic in numpy (field placement, plane skipping), plane passes through the emulated kernel."""
     off = cuda.resolve_offset(order, parity)
     sb = planes[0].dtype.itemsize
@@ -54,7 +54,7 @@ def emulate(L, planes, bits, order=1, aa=48, aac=0, dh=False, luma=True, chroma=
                           (C.c_longlong * n)(*[outs[p].strides[0] for p in proc]), (C.c_int * n)(*[outs[p].shape[1] for p in proc]),
                           (C.c_int * n)(*[outs[p].shape[0] for p in proc]), (C.c_int * n)(*[off] * n),
                           (C.c_float * n)(*[cuda.threshold(aa if p == 0 else aac, bits, sb) for p in proc]),
-                          outs[0].shape[1], outs[0].shape[0])
+                          outs[0].shape[1], outs[0].shape[0], cluster)
         assert rc == 0
     return outs
 
@@ -71,6 +71,13 @@ EMUL_CASES = [
     ("YUV422P8", 68, 30, dict(order=2, aa=30, aac=90), "noise"), ("YV411", 64, 32, dict(order=1, aa=48, aac=30), "edges"),
     ("YV24", 44, 20, dict(dh=True, aa=48, aac=48), "noise"), ("YV12", 352, 64, dict(order=0, aa=48, aac=48), "edges"),
     ("Y8", 16, 8, dict(order=1, aa=0), "edges"),
+    # 16-bit and fp32 flavours
+    ("Y16", 40, 12, dict(order=1), "noise"), ("Y10", 33, 10, dict(order=2, aa=100), "edges"), ("YUV420P16", 96, 48, dict(order=0, aa=48, aac=48), "noise"),
+    ("YUV420P10", 100, 40, dict(order=1, aa=48, aac=20), "edges"), ("YUV422P10", 68, 30, dict(order=2, aa=30, aac=90), "noise"),
+    ("YUV444P16", 44, 20, dict(dh=True, aa=48, aac=48), "noise"), ("YUV420P16", 72, 40, dict(luma=False, aa=48, aac=48), "noise"),
+    ("Y32", 40, 12, dict(order=1), "noise"), ("YUV420PS", 96, 48, dict(order=2, aa=48, aac=24), "noise"),
+    ("YUV420PS", 100, 40, dict(order=0, aa=48, aac=24), "edges"), ("YUV444PS", 44, 20, dict(dh=True, aa=128, aac=128), "edges"),
+    ("YUV422PS", 68, 30, dict(order=1, aa=10, aac=0), "noise"),
 ]
 
 
@@ -82,3 +89,19 @@ def test_emulated_kernel_matches_oracle(emul, fmtname, w, h, kw, kind):
         got = emulate(emul, fr, fmt.bits, parity=(i == 0), **kw)
         exp = O.oracle_frame(fr, fmt.bits, parity=(i == 0), **kw)
         assert_planes_equal(got, exp[:3], f"{fmtname} {w}x{h} {kw} frame {i}")
+
+
+CLUSTER_CASES = [("Y8", 120, 20, dict(order=1), 2), ("YV12", 250, 36, dict(order=0, aa=48, aac=48), 4), ("Y8", 64, 12, dict(order=2, aa=20), 8),
+                 ("Y16", 120, 20, dict(order=1), 2), ("YUV420P10", 250, 36, dict(order=0, aa=48, aac=48), 4), ("YUV420PS", 120, 24, dict(order=2, aa=48, aac=24), 2),
+                 ("Y32", 64, 12, dict(order=1), 8), ("YUV422P16", 68, 30, dict(order=2, aa=30, aac=90), 2)]
+
+
+@pytest.mark.parametrize("fmtname,w,h,kw,cluster", CLUSTER_CASES, ids=[f"{c[0]}_{c[1]}x{c[2]}_G{c[4]}" for c in CLUSTER_CASES])
+def test_cluster_split_matches_oracle(emul, fmtname, w, h, kw, cluster):
+    """A plane split into column segments over the blocks of a cluster (DSMEM halo + cluster barrier) gives the
+    same bytes as the unsplit plane - i.e. as the oracle."""
+    fmt = FORMATS[fmtname]
+    fr = make_frame(41, w, h, fmt, "noise", 0)
+    got = emulate(emul, fr, fmt.bits, cluster=cluster, **kw)
+    exp = O.oracle_frame(fr, fmt.bits, **kw)
+    assert_planes_equal(got, exp[:3], f"{fmtname} {w}x{h} {kw} G={cluster}")
