@@ -61,10 +61,16 @@ struct Pass {
     int W, H, n;             // samples, rows, kept rows
     int R;                   // pool rows to sweep
     sn::CostState in{}, out{};
-    // device placement (host path)
-    size_t dev_off = 0;      // byte offset of the plane inside the chunk's plane buffer
-    size_t dev_pitch = 0;    // bytes
-    // staging placement for pageable host memory
+    // host path: how the kept field gets up and the finished plane gets down.
+    //   STAGED  pageable host memory: CPU packs rows into the slot's pinned staging, one contiguous DMA
+    //   LINEAR  pinned, rows contiguous and 16-byte multiples: one contiguous DMA straight from/to user memory
+    //           (upload: the whole source plane - a strided kept-field copy runs ~8x slower on this DMA engine)
+    //   PITCHED pinned, anything else: 2-D DMA
+    enum Xfer { STAGED, LINEAR, PITCHED };
+    Xfer up = STAGED, down = STAGED;
+    size_t src_off = 0, src_bytes = 0, src_pitch = 0;   // device copy of the source rows (bytes)
+    size_t src_first = 0, src_step = 0;                 // kept row 0 and kept-row step inside it (bytes)
+    size_t dst_off = 0, dst_pitch = 0;                  // device dst plane
     size_t stage_in_off = 0, stage_out_off = 0;
     bool src_pinned = false, dst_pinned = false;
 };
@@ -82,7 +88,7 @@ struct Slot {
     DevBuf planes, state, tasks;
     PinnedBuf tasks_host, stage_in, stage_out;
     cudaStream_t compute = nullptr;
-    cudaEvent_t h2d_done = nullptr, kernels_done = nullptr, d2h_done = nullptr;
+    cudaEvent_t h2d_start = nullptr, h2d_done = nullptr, k_start = nullptr, kernels_done = nullptr, d2h_start = nullptr, d2h_done = nullptr;
     bool busy = false;
     std::vector<FramePlan*> frames;      // frames of the chunk in flight (for the pageable copy-out)
 };
@@ -98,6 +104,7 @@ struct sn_ctx {
     int S = 0, Hb = 0;
     int frames_in_flight = 0;
     cudaStream_t h2d = nullptr, d2h = nullptr, own_compute = nullptr;
+    cudaEvent_t trace_base = nullptr;
     Slot slots[kSlots];
     // device-entry resources
     DevBuf dev_state;
@@ -195,11 +202,15 @@ void place_state(FramePlan& f, char* base)
     for (Pass& p : f.passes) { sn::plan_place_state(p.in, base); sn::plan_place_state(p.out, base); }
 }
 
-sn::PlaneTask make_task(const sn_ctx* ctx, const Pass& p, void* plane, size_t pitch_bytes)
+sn::PlaneTask make_task(const sn_ctx* ctx, const Pass& p, void* plane, size_t pitch_bytes, const void* kept0, size_t kept_step_bytes)
 {
     sn::PlaneTask t{};
     t.plane = plane;
     t.pitch = (long long)(pitch_bytes / ctx->sample_bytes);
+    t.src = kept0;
+    t.src_pitch = (long long)(kept_step_bytes / ctx->sample_bytes);
+    // in place when the kept rows already sit at rows offset, offset+2, .. of the dst plane
+    t.copy_kept = !(kept0 == static_cast<char*>(plane) + (size_t)p.job->offset * pitch_bytes && kept_step_bytes == 2 * pitch_bytes);
     t.width = p.W; t.height = p.H; t.offset = p.job->offset;
     t.kept_rows = p.n; t.sweep_rows = p.R;
     t.thr_f = p.job->threshold;
@@ -222,13 +233,18 @@ void host_copy_plane(const sn_plane_job& jb, int sb)
 
 // Launch the passes of a set of frames: one kernel per pass index (all first planes, then all
 // second planes, ...), stream-ordered so pass q+1 of a frame sees pass q's cost state.
-int launch_passes(sn_ctx* ctx, const std::vector<std::vector<sn::PlaneTask>>& by_pass, sn::PlaneTask* host_tasks,
-                  sn::PlaneTask* dev_tasks, cudaStream_t stream)
+int upload_tasks(sn_ctx* ctx, const std::vector<std::vector<sn::PlaneTask>>& by_pass, sn::PlaneTask* host_tasks,
+                 sn::PlaneTask* dev_tasks, cudaStream_t stream)
 {
     size_t total = 0;
     for (auto& v : by_pass) { std::memcpy(host_tasks + total, v.data(), v.size() * sizeof(sn::PlaneTask)); total += v.size(); }
     if (total == 0) return SN_OK;
     SN_CUDA(ctx, cudaMemcpyAsync(dev_tasks, host_tasks, total * sizeof(sn::PlaneTask), cudaMemcpyHostToDevice, stream));
+    return SN_OK;
+}
+
+int launch_passes(sn_ctx* ctx, const std::vector<std::vector<sn::PlaneTask>>& by_pass, sn::PlaneTask* dev_tasks, cudaStream_t stream)
+{
     size_t pos = 0;
     for (auto& v : by_pass) {
         if (v.empty()) continue;
@@ -245,14 +261,26 @@ int drain_slot(sn_ctx* ctx, Slot& s)
 {
     if (!s.busy) return SN_OK;
     SN_CUDA(ctx, cudaEventSynchronize(s.d2h_done));
+    static const bool trace = getenv("SANGNOM_TRACE") != nullptr;
+    if (trace) {
+        float t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
+        cudaEventElapsedTime(&t0, ctx->trace_base, s.h2d_start);
+        cudaEventElapsedTime(&t1, ctx->trace_base, s.h2d_done);
+        cudaEventElapsedTime(&t2, ctx->trace_base, s.k_start);
+        cudaEventElapsedTime(&t3, ctx->trace_base, s.kernels_done);
+        cudaEventElapsedTime(&t4, ctx->trace_base, s.d2h_start);
+        cudaEventElapsedTime(&t5, ctx->trace_base, s.d2h_done);
+        fprintf(stderr, "[sangnom] chunk of %3zu frames: h2d %6.2f..%6.2f  kernels %6.2f..%6.2f  d2h %6.2f..%6.2f ms\n",
+                s.frames.size(), t0, t1, t2, t3, t4, t5);
+    }
     const int sb = ctx->sample_bytes;
     for (FramePlan* f : s.frames)
         for (Pass& p : f->passes) {
-            if (p.dst_pinned) continue;
+            if (p.down != Pass::STAGED) continue;
             const sn_plane_job& jb = *p.job;
             const size_t row = (size_t)p.W * sb;
             const char* st = static_cast<const char*>(s.stage_out.p) + p.stage_out_off;
-            for (int y = 0; y < p.H; ++y) std::memcpy(static_cast<char*>(jb.dst) + (ptrdiff_t)y * jb.dst_pitch, st + (size_t)y * row, row);
+            for (int y = 0; y < p.H; ++y) std::memcpy(static_cast<char*>(jb.dst) + (ptrdiff_t)y * jb.dst_pitch, st + (size_t)y * p.dst_pitch, row);
         }
     s.frames.clear();
     s.busy = false;
@@ -338,7 +366,15 @@ int sangnom_cuda_create(const sn_config* cfg, sn_ctx** out)
     ctx->cfg = *cfg;
     ctx->sample_bytes = cfg->sample_type;
     ctx->S = S; ctx->Hb = Hb;
-    ctx->frames_in_flight = cfg->max_frames_in_flight > 0 ? cfg->max_frames_in_flight : 96;
+    if (cfg->max_frames_in_flight > 0) {
+        ctx->frames_in_flight = cfg->max_frames_in_flight;
+    } else {
+        // default: three chunks of one frame per SM (so every launch can fill the GPU), capped at ~6 GB of
+        // device memory for planes + cost state (about 2.5 x the three planes of a frame)
+        const double per_frame = 2.5 * 3.0 * (double)S * (double)cfg->pool_height * (double)cfg->sample_type;
+        const long long fit = (long long)(6.0e9 / per_frame);
+        ctx->frames_in_flight = (int)std::min<long long>(3LL * prop.multiProcessorCount, std::max<long long>(fit, 12));
+    }
     auto bail = [&](cudaError_t err, const char* what) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
         sangnom_cuda_destroy(ctx);
@@ -350,12 +386,16 @@ int sangnom_cuda_create(const sn_config* cfg, sn_ctx** out)
     if ((e = cudaStreamCreateWithFlags(&ctx->own_compute, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     for (Slot& s : ctx->slots) {
         if ((e = cudaStreamCreateWithFlags(&s.compute, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
-        if ((e = cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
-        if ((e = cudaEventCreateWithFlags(&s.kernels_done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
-        if ((e = cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+        if ((e = cudaEventCreate(&s.h2d_start)) != cudaSuccess) return bail(e, "cudaEventCreate");
+        if ((e = cudaEventCreate(&s.k_start)) != cudaSuccess) return bail(e, "cudaEventCreate");
+        if ((e = cudaEventCreate(&s.d2h_start)) != cudaSuccess) return bail(e, "cudaEventCreate");
+        if ((e = cudaEventCreate(&s.h2d_done)) != cudaSuccess) return bail(e, "cudaEventCreate");
+        if ((e = cudaEventCreate(&s.kernels_done)) != cudaSuccess) return bail(e, "cudaEventCreate");
+        if ((e = cudaEventCreate(&s.d2h_done)) != cudaSuccess) return bail(e, "cudaEventCreate");
     }
     for (int i = 0; i < kTaskRing; ++i)
         if ((e = cudaEventCreateWithFlags(&ctx->dev_task_free[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&ctx->trace_base)) != cudaSuccess) return bail(e, "cudaEventCreate");
     *out = ctx;
     return SN_OK;
 }
@@ -369,6 +409,9 @@ void sangnom_cuda_destroy(sn_ctx* ctx)
         s.planes.release(); s.state.release(); s.tasks.release();
         s.tasks_host.release(); s.stage_in.release(); s.stage_out.release();
         if (s.compute) cudaStreamDestroy(s.compute);
+        if (s.h2d_start) cudaEventDestroy(s.h2d_start);
+        if (s.k_start) cudaEventDestroy(s.k_start);
+        if (s.d2h_start) cudaEventDestroy(s.d2h_start);
         if (s.h2d_done) cudaEventDestroy(s.h2d_done);
         if (s.kernels_done) cudaEventDestroy(s.kernels_done);
         if (s.d2h_done) cudaEventDestroy(s.d2h_done);
@@ -379,6 +422,7 @@ void sangnom_cuda_destroy(sn_ctx* ctx)
         ctx->dev_tasks_host[i].release();
         if (ctx->dev_task_free[i]) cudaEventDestroy(ctx->dev_task_free[i]);
     }
+    if (ctx->trace_base) cudaEventDestroy(ctx->trace_base);
     if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
     if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
     if (ctx->own_compute) cudaStreamDestroy(ctx->own_compute);
@@ -438,7 +482,8 @@ int sangnom_cuda_process_planes_device(sn_ctx* ctx, const sn_plane_job* jobs, in
         SN_CUDA(ctx, ctx->dev_state.ensure(state_total));
     }
 
-    // plane copies / kept-field placement
+    // whole-plane copies of unprocessed planes; processed planes need no copy at all: the kernel reads the
+    // kept rows where they are and writes them into dst itself when they are not already there
     for (FramePlan& f : frames) {
         for (const sn_plane_job* c : f.copies) {
             if (c->src == c->dst) continue;
@@ -446,23 +491,22 @@ int sangnom_cuda_process_planes_device(sn_ctx* ctx, const sn_plane_job* jobs, in
                                            (size_t)c->dst_height, cudaMemcpyDeviceToDevice, stream));
         }
         place_state(f, static_cast<char*>(ctx->dev_state.p) + f.state_off);
-        for (Pass& p : f.passes) {
-            const sn_plane_job& jb = *p.job;
-            if (jb.mode == SN_MODE_INPLACE) continue;
-            const char* src = static_cast<const char*>(jb.src) + (jb.mode == SN_MODE_FIELD ? (ptrdiff_t)jb.offset * jb.src_pitch : 0);
-            const size_t spitch = (size_t)jb.src_pitch * (jb.mode == SN_MODE_FIELD ? 2 : 1);
-            char* dst = static_cast<char*>(jb.dst) + (ptrdiff_t)jb.offset * jb.dst_pitch;
-            if (src != dst)
-                SN_CUDA(ctx, cudaMemcpy2DAsync(dst, (size_t)jb.dst_pitch * 2, src, spitch, (size_t)p.W * sb, (size_t)p.n,
-                                               cudaMemcpyDeviceToDevice, stream));
-        }
     }
 
     const auto t2 = now();
     std::vector<std::vector<sn::PlaneTask>> by_pass(3);
     for (FramePlan& f : frames)
         for (size_t q = 0; q < f.passes.size(); ++q)
-            by_pass[q].push_back(make_task(ctx, f.passes[q], f.passes[q].job->dst, (size_t)f.passes[q].job->dst_pitch));
+        {
+            const Pass& p = f.passes[q];
+            const sn_plane_job& jb = *p.job;
+            const char* kept0;
+            size_t step;
+            if (jb.mode == SN_MODE_INPLACE) { kept0 = static_cast<const char*>(jb.dst) + (ptrdiff_t)jb.offset * jb.dst_pitch; step = 2 * (size_t)jb.dst_pitch; }
+            else if (jb.mode == SN_MODE_FIELD) { kept0 = static_cast<const char*>(jb.src) + (ptrdiff_t)jb.offset * jb.src_pitch; step = 2 * (size_t)jb.src_pitch; }
+            else { kept0 = static_cast<const char*>(jb.src); step = (size_t)jb.src_pitch; }
+            by_pass[q].push_back(make_task(ctx, p, jb.dst, (size_t)jb.dst_pitch, kept0, step));
+        }
     const auto t3 = now();
 
     // Task arrays travel through a small ring of pinned/device buffers; all entries are grown
@@ -479,8 +523,10 @@ int sangnom_cuda_process_planes_device(sn_ctx* ctx, const sn_plane_job* jobs, in
     const int slot = ctx->dev_ring_pos;
     ctx->dev_ring_pos = (ctx->dev_ring_pos + 1) % kTaskRing;
     SN_CUDA(ctx, cudaEventSynchronize(ctx->dev_task_free[slot]));     // ring entry no longer read by an earlier upload
-    rc = launch_passes(ctx, by_pass, static_cast<sn::PlaneTask*>(ctx->dev_tasks_host[slot].p),
-                       static_cast<sn::PlaneTask*>(ctx->dev_tasks[slot].p), stream);
+    rc = upload_tasks(ctx, by_pass, static_cast<sn::PlaneTask*>(ctx->dev_tasks_host[slot].p),
+                      static_cast<sn::PlaneTask*>(ctx->dev_tasks[slot].p), stream);
+    if (rc != SN_OK) return rc;
+    rc = launch_passes(ctx, by_pass, static_cast<sn::PlaneTask*>(ctx->dev_tasks[slot].p), stream);
     if (rc != SN_OK) return rc;
     SN_CUDA(ctx, cudaEventRecord(ctx->dev_task_free[slot], stream));
     ctx->stats.frames += frames.size();
@@ -513,6 +559,7 @@ int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs
             p.dst_pinned = is_pinned_host(p.job->dst);
         }
 
+    cudaEventRecord(ctx->trace_base, ctx->h2d);
     const size_t chunk_frames = std::max<size_t>(1, (size_t)ctx->frames_in_flight / kSlots);
     size_t next = 0;
     int slot_idx = 0;
@@ -532,11 +579,24 @@ int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs
             f.state_off = state_bytes;
             state_bytes += align_up(f.state_bytes, 256);
             for (Pass& p : f.passes) {
-                p.dev_pitch = align_up((size_t)p.W * sb, 256);
-                p.dev_off = plane_bytes;
-                plane_bytes += p.dev_pitch * p.H;
-                if (!p.src_pinned) { p.stage_in_off = in_bytes; in_bytes += align_up((size_t)p.W * sb * p.n, 256); }
-                if (!p.dst_pinned) { p.stage_out_off = out_bytes; out_bytes += align_up((size_t)p.W * sb * p.H, 256); }
+                const sn_plane_job& jb = *p.job;
+                const size_t row = (size_t)p.W * sb, rowpad = align_up(row, 16);
+                const int src_rows = jb.mode == SN_MODE_FIELD ? p.H : p.n;
+                const bool field = jb.mode == SN_MODE_FIELD;
+                if (!p.src_pinned) {                                   // kept rows packed by the CPU
+                    p.up = Pass::STAGED; p.src_pitch = rowpad; p.src_bytes = rowpad * p.n; p.src_first = 0; p.src_step = rowpad;
+                    p.stage_in_off = in_bytes; in_bytes += align_up(p.src_bytes, 256);
+                } else if ((size_t)jb.src_pitch == row && row % 16 == 0) {   // whole source plane, one contiguous DMA
+                    p.up = Pass::LINEAR; p.src_pitch = row; p.src_bytes = row * src_rows;
+                    p.src_first = field ? (size_t)jb.offset * row : 0; p.src_step = field ? 2 * row : row;
+                } else {                                               // kept rows by 2-D DMA
+                    p.up = Pass::PITCHED; p.src_pitch = rowpad; p.src_bytes = rowpad * p.n; p.src_first = 0; p.src_step = rowpad;
+                }
+                p.src_off = plane_bytes; plane_bytes += align_up(p.src_bytes, 256);
+                if (!p.dst_pinned) { p.down = Pass::STAGED; p.dst_pitch = rowpad; p.stage_out_off = out_bytes; out_bytes += align_up(rowpad * p.H, 256); }
+                else if ((size_t)jb.dst_pitch == row && row % 16 == 0) { p.down = Pass::LINEAR; p.dst_pitch = row; }
+                else { p.down = Pass::PITCHED; p.dst_pitch = rowpad; }
+                p.dst_off = plane_bytes; plane_bytes += align_up(p.dst_pitch * p.H, 256);
                 ++ntasks;
             }
         }
@@ -549,7 +609,8 @@ int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs
             break;
         }
 
-        // ---- upload the kept fields (the reference's BitBlt :361-377, as a strided DMA) ----
+        cudaEventRecord(s.h2d_start, ctx->h2d);
+        // ---- upload (the reference's kept-field BitBlt, SangNom2.cpp:361-377, becomes DMA + the kernel's own reads) ----
         std::vector<std::vector<sn::PlaneTask>> by_pass(3);
         for (size_t k = first; k < last && status == SN_OK; ++k) {
             FramePlan& f = frames[k];
@@ -559,46 +620,55 @@ int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs
                 Pass& p = f.passes[q];
                 const sn_plane_job& jb = *p.job;
                 const size_t row = (size_t)p.W * sb;
-                const char* src = static_cast<const char*>(jb.src) + (jb.mode == SN_MODE_FIELD ? (ptrdiff_t)jb.offset * jb.src_pitch : 0);
-                size_t spitch = (size_t)jb.src_pitch * (jb.mode == SN_MODE_FIELD ? 2 : 1);
-                if (!p.src_pinned) {
+                const char* kept = static_cast<const char*>(jb.src) + (jb.mode == SN_MODE_FIELD ? (ptrdiff_t)jb.offset * jb.src_pitch : 0);
+                const size_t kept_step = (size_t)jb.src_pitch * (jb.mode == SN_MODE_FIELD ? 2 : 1);
+                char* dsrc = static_cast<char*>(s.planes.p) + p.src_off;
+                if (p.up == Pass::STAGED) {
                     char* st = static_cast<char*>(s.stage_in.p) + p.stage_in_off;
-                    for (int y = 0; y < p.n; ++y) std::memcpy(st + (size_t)y * row, src + (size_t)y * spitch, row);
-                    src = st; spitch = row;
+                    for (int y = 0; y < p.n; ++y) std::memcpy(st + (size_t)y * p.src_pitch, kept + (size_t)y * kept_step, row);
+                    e = cudaMemcpyAsync(dsrc, st, p.src_bytes, cudaMemcpyHostToDevice, ctx->h2d);
+                } else if (p.up == Pass::LINEAR) {
+                    e = cudaMemcpyAsync(dsrc, jb.src, p.src_bytes, cudaMemcpyHostToDevice, ctx->h2d);
+                } else {
+                    e = cudaMemcpy2DAsync(dsrc, p.src_pitch, kept, kept_step, row, (size_t)p.n, cudaMemcpyHostToDevice, ctx->h2d);
                 }
-                char* dplane = static_cast<char*>(s.planes.p) + p.dev_off;
-                e = cudaMemcpy2DAsync(dplane + (size_t)jb.offset * p.dev_pitch, p.dev_pitch * 2, src, spitch, row, (size_t)p.n,
-                                      cudaMemcpyHostToDevice, ctx->h2d);
                 if (e != cudaSuccess) { status = ctx->cuda_fail(e, "H2D copy"); break; }
-                ctx->stats.h2d_bytes += row * p.n;
-                by_pass[q].push_back(make_task(ctx, p, dplane, p.dev_pitch));
+                ctx->stats.h2d_bytes += p.up == Pass::PITCHED ? row * p.n : p.src_bytes;
+                by_pass[q].push_back(make_task(ctx, p, static_cast<char*>(s.planes.p) + p.dst_off, p.dst_pitch, dsrc + p.src_first, p.src_step));
             }
         }
         if (status != SN_OK) break;
+        // The task array rides the upload stream too: a small copy on the compute stream would queue on the
+        // same DMA engine behind the NEXT chunks' bulk uploads and hold this chunk's kernels back.
+        if ((status = upload_tasks(ctx, by_pass, static_cast<sn::PlaneTask*>(s.tasks_host.p), static_cast<sn::PlaneTask*>(s.tasks.p), ctx->h2d)) != SN_OK) break;
         if ((e = cudaEventRecord(s.h2d_done, ctx->h2d)) != cudaSuccess || (e = cudaStreamWaitEvent(s.compute, s.h2d_done, 0)) != cudaSuccess) {
             status = ctx->cuda_fail(e, "event"); break;
         }
 
         // ---- kernels ----
-        status = launch_passes(ctx, by_pass, static_cast<sn::PlaneTask*>(s.tasks_host.p), static_cast<sn::PlaneTask*>(s.tasks.p), s.compute);
+        cudaEventRecord(s.k_start, s.compute);
+        status = launch_passes(ctx, by_pass, static_cast<sn::PlaneTask*>(s.tasks.p), s.compute);
         if (status != SN_OK) break;
         if ((e = cudaEventRecord(s.kernels_done, s.compute)) != cudaSuccess || (e = cudaStreamWaitEvent(ctx->d2h, s.kernels_done, 0)) != cudaSuccess) {
             status = ctx->cuda_fail(e, "event"); break;
         }
 
         // ---- download ----
+        cudaEventRecord(s.d2h_start, ctx->d2h);
         for (size_t k = first; k < last && status == SN_OK; ++k) {
             FramePlan& f = frames[k];
             for (Pass& p : f.passes) {
                 const sn_plane_job& jb = *p.job;
                 const size_t row = (size_t)p.W * sb;
-                char* dst = static_cast<char*>(jb.dst);
-                size_t dpitch = (size_t)jb.dst_pitch;
-                if (!p.dst_pinned) { dst = static_cast<char*>(s.stage_out.p) + p.stage_out_off; dpitch = row; }
-                e = cudaMemcpy2DAsync(dst, dpitch, static_cast<char*>(s.planes.p) + p.dev_off, p.dev_pitch, row, (size_t)p.H,
-                                      cudaMemcpyDeviceToHost, ctx->d2h);
+                const char* dplane = static_cast<char*>(s.planes.p) + p.dst_off;
+                if (p.down == Pass::STAGED)
+                    e = cudaMemcpyAsync(static_cast<char*>(s.stage_out.p) + p.stage_out_off, dplane, p.dst_pitch * p.H, cudaMemcpyDeviceToHost, ctx->d2h);
+                else if (p.down == Pass::LINEAR)
+                    e = cudaMemcpyAsync(jb.dst, dplane, row * p.H, cudaMemcpyDeviceToHost, ctx->d2h);
+                else
+                    e = cudaMemcpy2DAsync(jb.dst, (size_t)jb.dst_pitch, dplane, p.dst_pitch, row, (size_t)p.H, cudaMemcpyDeviceToHost, ctx->d2h);
                 if (e != cudaSuccess) { status = ctx->cuda_fail(e, "D2H copy"); break; }
-                ctx->stats.d2h_bytes += row * p.H;
+                ctx->stats.d2h_bytes += p.down == Pass::PITCHED ? row * p.H : p.dst_pitch * p.H;
             }
             s.frames.push_back(&f);
         }

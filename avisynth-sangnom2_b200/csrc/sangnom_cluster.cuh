@@ -46,11 +46,5 @@ __device__ __forceinline__ void store_remote(V* local_ptr, unsigned target_rank,
 }
 #endif
 
-// the row barrier: block-wide for a plane in one block, cluster-wide when the plane is split
-__device__ __forceinline__ void row_barrier(bool clustered)
-{
-    if (clustered) sync_all(); else __syncthreads();
-}
-
 }  // namespace cl
 }  // namespace sn

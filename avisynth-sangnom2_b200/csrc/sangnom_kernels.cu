@@ -72,9 +72,15 @@ cudaError_t launch_u8(const PlaneTask* tasks, int ntasks, LaunchGeometry g, cuda
     const int seg = g.S / G;
     if (seg > 2048 || seg % u8k::kCols != 0) return cudaErrorInvalidValue;
     const size_t smem = u8k::smem_bytes(seg);
-    auto kernel = u8k::sangnom_u8_row_sweep<256, 2>;
-    static size_t configured[64] = {};
-    cudaError_t e = ensure_smem(kernel, smem, configured);
+    static size_t configured[2][64] = {};
+    if (G == 1) {
+        auto kernel = u8k::sangnom_u8_row_sweep<256, 2, false>;
+        cudaError_t e = ensure_smem(kernel, smem, configured[0]);
+        if (e != cudaSuccess) return e;
+        return launch_clustered(kernel, ntasks, seg / u8k::kCols, smem, 1, stream, tasks, g, seg);
+    }
+    auto kernel = u8k::sangnom_u8_row_sweep<256, 2, true>;
+    cudaError_t e = ensure_smem(kernel, smem, configured[1]);
     if (e != cudaSuccess) return e;
     return launch_clustered(kernel, ntasks * G, seg / u8k::kCols, smem, G, stream, tasks, g, seg);
 }
@@ -88,9 +94,15 @@ cudaError_t launch_wide(const PlaneTask* tasks, int ntasks, LaunchGeometry g, cu
     const int seg = g.S / G;
     if (seg > 1024 || seg % wide::kCols != 0) return cudaErrorInvalidValue;
     const size_t smem = wide::smem_bytes<T>(seg);
-    auto kernel = wide::sangnom_wide_row_sweep<T, 256, 2>;
-    static size_t configured[64] = {};
-    cudaError_t e = ensure_smem(kernel, smem, configured);
+    static size_t configured[2][64] = {};
+    if (G == 1) {
+        auto kernel = wide::sangnom_wide_row_sweep<T, 256, 2, false>;
+        cudaError_t e = ensure_smem(kernel, smem, configured[0]);
+        if (e != cudaSuccess) return e;
+        return launch_clustered(kernel, ntasks, seg / wide::kCols, smem, 1, stream, tasks, g, seg);
+    }
+    auto kernel = wide::sangnom_wide_row_sweep<T, 256, 2, true>;
+    cudaError_t e = ensure_smem(kernel, smem, configured[1]);
     if (e != cudaSuccess) return e;
     return launch_clustered(kernel, ntasks * G, seg / wide::kCols, smem, G, stream, tasks, g, seg);
 }

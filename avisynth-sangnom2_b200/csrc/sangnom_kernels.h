@@ -24,8 +24,11 @@ struct CostState {
 
 // One plane pass = one thread block sweeping pool rows 1..sweep_rows over all S pool columns.
 struct PlaneTask {
-    void* plane;            // device pointer to row 0 of the dst plane (kept field already in place)
+    void* plane;            // device pointer to row 0 of the dst plane
     long long pitch;        // elements
+    const void* src;        // device pointer to kept row 0 (reference: the rows the BitBlt at GetFrame :361-377 copies)
+    long long src_pitch;    // elements between consecutive kept rows. In place: src = plane + offset*pitch, src_pitch = 2*pitch
+    int copy_kept;          // 1: the kept rows are not in the dst plane yet - the kernel writes them too
     int width;              // W: samples per row that carry pixels (cost rectangle width)
     int height;             // H: rows of the dst plane
     int offset;             // 0 / 1: first kept row

@@ -215,15 +215,14 @@ __device__ __forceinline__ uint2 interpolate8(const Taps& c, const Taps& n, cons
     return out;
 }
 
-template <int kMaxThreads, int kMinBlocks>
+template <int kMaxThreads, int kMinBlocks, bool kClustered>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
 sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int seg_cols)
 {
     SN_DYNAMIC_SMEM(smem_raw);
     // a plane wider than one block is split into column segments over the blocks of a cluster
-    const unsigned G = cl::size();
-    const unsigned crank = cl::rank();
-    const bool clustered = G > 1;
+    const unsigned G = kClustered ? cl::size() : 1u;      // kClustered = false: one block per plane, no cluster code at all
+    const unsigned crank = kClustered ? cl::rank() : 0u;
     const PlaneTask t = tasks[blockIdx.x / G];
     const int S = g.S;
     const int LS = seg_cols + 2 * kLPad;                            // u16 elements per shared L row of this segment
@@ -235,27 +234,33 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     const bool plane_first = x0 == 0, plane_last = x0 + kCols == S;
     const bool seg_first = lx == 0, seg_last = lx + kCols == seg_cols;
     uint8_t* const plane = static_cast<uint8_t*>(t.plane);
-    const long long pitch = t.pitch;
-    const bool vec = ((reinterpret_cast<uintptr_t>(plane) | (uintptr_t)pitch) & 15) == 0 && pitch >= (((long long)W + 15) & ~15LL);
+    const uint8_t* const src = static_cast<const uint8_t*>(t.src);
+    const long long pitch = t.pitch, src_pitch = t.src_pitch;
+    const long long wpad = ((long long)W + 15) & ~15LL;
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)src_pitch) & 15) == 0 && src_pitch >= wpad;      // aligned vector loads of kept rows
+    const bool vec_out = ((reinterpret_cast<uintptr_t>(plane) | (uintptr_t)pitch) & 15) == 0 && pitch >= wpad;        // aligned vector stores
     // which of my 8 columns carry pixels: all, none, or a prefix (the one thread that straddles W)
     const int npix = min(max(W - x0, 0), kCols);
     const uint32_t pixmask_lo = npix >= 4 ? 0xFFFFFFFFu : (npix <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - npix))));
     const uint32_t pixmask_hi = npix >= 8 ? 0xFFFFFFFFu : (npix <= 4 ? 0u : (0xFFFFFFFFu >> (8 * (8 - npix))));
 
-    auto kept_row = [&](int j) -> const uint8_t* { return plane + (long long)(t.offset + 2 * j) * pitch; };
+    auto kept_row = [&](int j) -> const uint8_t* { return src + (long long)j * src_pitch; };
     auto store8 = [&](uint8_t* row, uint2 v) {
-        if (npix == kCols && vec) { *reinterpret_cast<uint2*>(row + x0) = v; return; }
+        if (npix == kCols && vec_out) { *reinterpret_cast<uint2*>(row + x0) = v; return; }
 #pragma unroll
         for (int b = 0; b < 8; ++b) if (b < npix) row[x0 + b] = (uint8_t)(((b < 4 ? v.x : v.y) >> (8 * (b & 3))) & 0xFFu);
     };
 
     // ---- border row without a neighbour pair (reference GetFrame :380-391) ----
     if (npix > 0) {
-        const uint8_t* from = t.offset == 0 ? plane + (long long)(t.height - 2) * pitch : plane + pitch;
         uint8_t* to = t.offset == 0 ? plane + (long long)(t.height - 1) * pitch : plane;
         uint32_t w[4];
-        load_window(from, x0, W, vec, w);
+        load_window(kept_row(t.offset == 0 ? n - 1 : 0), x0, W, vec, w);
         store8(to, make_uint2(w[1], w[2]));
+        if (t.copy_kept) {                       // last kept row; rows 0..n-2 are written as the sweep passes them
+            if (t.offset != 0) load_window(kept_row(n - 1), x0, W, vec, w);
+            store8(plane + (long long)(t.offset + 2 * (n - 1)) * pitch, make_uint2(w[1], w[2]));
+        }
     }
 
     // ---- running term M = B[r-1] + P[r]; B[0] = 0 so M starts as P[1] ----
@@ -335,7 +340,7 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
                 M[i][0] = P[i][0]; M[i][1] = P[i][1]; M[i][2] = P[i][2]; M[i][3] = P[i][3];
             }
         }
-        cl::row_barrier(clustered);
+        if constexpr (kClustered) cl::sync_all(); else __syncthreads();
 
         // ---- B[r] = wrap8(H7(L) >> 4) per buffer; keys for the min; M += B ----
         uint32_t kmin[4] = { tkey, tkey, tkey, tkey };
@@ -373,6 +378,7 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
             c.build(wa); nx.build(wb);
             const uint2 px = interpolate8(c, nx, sg_prev, kmin);
             store8(plane + (long long)(t.offset + 2 * (r - 1) + 1) * pitch, px);
+            if (t.copy_kept) store8(plane + (long long)(t.offset + 2 * (r - 1)) * pitch, make_uint2(wa[1], wa[2]));
         }
 
 #pragma unroll

@@ -76,16 +76,15 @@ __device__ __forceinline__ void load_window(const T* __restrict__ row, int x0, i
     for (int e = kHalo + 1; e < kWin; ++e) if (e > last) w[e] = w[e - 1];
 }
 
-template <typename T, int kMaxThreads, int kMinBlocks>
+template <typename T, int kMaxThreads, int kMinBlocks, bool kClustered>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
 sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int seg_cols)
 {
     using I = typename Flavour<T>::I;
     SN_DYNAMIC_SMEM(smem_raw);
 
-    const unsigned G = cl::size();
-    const unsigned crank = cl::rank();
-    const bool clustered = G > 1;
+    const unsigned G = kClustered ? cl::size() : 1u;      // kClustered = false: one block per plane, no cluster code at all
+    const unsigned crank = kClustered ? cl::rank() : 0u;
     const PlaneTask t = tasks[blockIdx.x / G];
     const int S = g.S;
     const int LS = seg_cols + 2 * kHalo;                         // elements per shared L row of this segment
@@ -97,26 +96,34 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
     const bool plane_first = x0 == 0, plane_last = x0 + kCols == S;
     const bool seg_first = lx == 0, seg_last = lx + kCols == seg_cols;
     T* const plane = static_cast<T*>(t.plane);
-    const long long pitch = t.pitch;
-    const bool vec = ((reinterpret_cast<uintptr_t>(plane) | (uintptr_t)(pitch * (long long)sizeof(T))) & 15) == 0 &&
-                     pitch * (long long)sizeof(T) >= (((long long)W * (long long)sizeof(T) + 15) & ~15LL);
+    const T* const src = static_cast<const T*>(t.src);
+    const long long pitch = t.pitch, src_pitch = t.src_pitch;
+    const long long wpad = ((long long)W * (long long)sizeof(T) + 15) & ~15LL;
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)(src_pitch * (long long)sizeof(T))) & 15) == 0 &&
+                     src_pitch * (long long)sizeof(T) >= wpad;                       // aligned vector loads of kept rows
+    const bool vec_out = ((reinterpret_cast<uintptr_t>(plane) | (uintptr_t)(pitch * (long long)sizeof(T))) & 15) == 0 &&
+                         pitch * (long long)sizeof(T) >= wpad;                       // aligned vector stores
     const int npix = min(max(W - x0, 0), kCols);                 // how many of my columns carry pixels
 
-    auto kept_row = [&](int j) -> const T* { return plane + (long long)(t.offset + 2 * j) * pitch; };
+    auto kept_row = [&](int j) -> const T* { return src + (long long)j * src_pitch; };
     auto store_px = [&](T* row, const I (&v)[4]) {
-        if (npix == kCols && vec) { store4(row + x0, v); return; }
+        if (npix == kCols && vec_out) { store4(row + x0, v); return; }
 #pragma unroll
         for (int c = 0; c < kCols; ++c) if (c < npix) row[x0 + c] = (T)v[c];
     };
 
     // ---- border row without a neighbour pair (reference GetFrame :380-391) ----
     if (npix > 0) {
-        const T* from = t.offset == 0 ? plane + (long long)(t.height - 2) * pitch : plane + pitch;
         T* to = t.offset == 0 ? plane + (long long)(t.height - 1) * pitch : plane;
         I w[kWin];
-        load_window<T, I>(from, x0, W, vec, w);
+        load_window<T, I>(kept_row(t.offset == 0 ? n - 1 : 0), x0, W, vec, w);
         const I own[4] = { w[4], w[5], w[6], w[7] };
         store_px(to, own);
+        if (t.copy_kept) {                       // last kept row; rows 0..n-2 are written as the sweep passes them
+            if (t.offset != 0) load_window<T, I>(kept_row(n - 1), x0, W, vec, w);
+            const I lastrow[4] = { w[4], w[5], w[6], w[7] };
+            store_px(plane + (long long)(t.offset + 2 * (n - 1)) * pitch, lastrow);
+        }
     }
 
     // Cost state of the previous pass at pool row `row` for my 4 columns: base pointer and per-buffer stride
@@ -197,7 +204,7 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
                        cl::store_remote(row - 1, crank + 1, L[3]); }
             }
         }
-        cl::row_barrier(clustered);
+        if constexpr (kClustered) cl::sync_all(); else __syncthreads();
 
         // ---- B[r] per cost buffer, min key, M = B[r] + P[r+1], hand-over ----
         size_t out_stride = 0;
@@ -262,6 +269,10 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
                 px[c] = interpolate_rank<T, I, kWin, kHalo>(wc, wn, c, rank);
             }
             store_px(plane + (long long)(t.offset + 2 * (r - 1) + 1) * pitch, px);
+            if (t.copy_kept) {
+                const I keptrow[4] = { wc[4], wc[5], wc[6], wc[7] };
+                store_px(plane + (long long)(t.offset + 2 * (r - 1)) * pitch, keptrow);
+            }
         }
     }
 }

@@ -40,7 +40,7 @@ WORKLOADS = {
     "480p8": ("YV12", 720, 480, dict(order=1, aa=48, chroma=False), "u8", 0),
 }
 DEFAULT_FRAMES = {"1080p8": 592, "2160pf32": 148, "2160p10": 148, "480p8": 1184}
-E2E_FRAMES = {"1080p8": 192, "2160pf32": 24, "2160p10": 48, "480p8": 768}
+E2E_FRAMES = {"1080p8": 592, "2160pf32": 48, "2160p10": 96, "480p8": 1184}
 
 
 def log(*a):
@@ -414,7 +414,7 @@ def main():
     ap.add_argument("--workload", default="1080p8", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="frames per step per GPU (device-resident leg)")
     ap.add_argument("--e2e-frames", type=int, default=0)
-    ap.add_argument("--in-flight", type=int, default=96, help="frames resident on the device in the host path")
+    ap.add_argument("--in-flight", type=int, default=0, help="frames resident on the device in the host path (0 = library default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

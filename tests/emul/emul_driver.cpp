@@ -13,7 +13,8 @@ extern "C" {
 
 // One frame: up to 3 processed planes, in place (kept field already in the dst planes).
 // planes[i]: pointer to row 0; pitch in BYTES; returns 0, or -1 for unsupported geometry.
-int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long long* pitch_bytes, const int* widths,
+int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long long* pitch_bytes, const void* const* srcs,
+               const long long* src_pitch_bytes, const int* widths,
                const int* heights, const int* offsets, const float* thresholds, int pool_width, int pool_height, int cluster)
 {
     const int S = (pool_width + 31) & ~31, Hb = (pool_height + 1) >> 1;
@@ -28,6 +29,15 @@ int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long lo
         sn::PlaneTask t{};
         t.plane = planes[q];
         t.pitch = pitch_bytes[q] / sample_bytes;
+        if (srcs && srcs[q]) {                  // out of place: kept rows come from a packed field buffer
+            t.src = srcs[q];
+            t.src_pitch = src_pitch_bytes[q] / sample_bytes;
+            t.copy_kept = 1;
+        } else {                                // in place: the kept field is already in the dst plane
+            t.src = static_cast<char*>(planes[q]) + (long long)offsets[q] * pitch_bytes[q];
+            t.src_pitch = 2 * t.pitch;
+            t.copy_kept = 0;
+        }
         t.width = widths[q]; t.height = heights[q]; t.offset = offsets[q];
         t.kept_rows = geo[q].kept_rows; t.sweep_rows = geo[q].sweep_rows;
         t.thr_f = thresholds[q];
@@ -40,11 +50,11 @@ int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long lo
         const int seg = S / (int)G;
         const unsigned threads = (unsigned)(seg / cols);
         if (sample_bytes == 1)
-            emul::run_cluster(0, G, threads, sn::u8k::smem_bytes(seg), [&] { sn::u8k::sangnom_u8_row_sweep<1024, 1>(&t, g, seg); });
+            emul::run_cluster(0, G, threads, sn::u8k::smem_bytes(seg), [&] { sn::u8k::sangnom_u8_row_sweep<1024, 1, true>(&t, g, seg); });
         else if (sample_bytes == 2)
-            emul::run_cluster(0, G, threads, sn::wide::smem_bytes<uint16_t>(seg), [&] { sn::wide::sangnom_wide_row_sweep<uint16_t, 1024, 1>(&t, g, seg); });
+            emul::run_cluster(0, G, threads, sn::wide::smem_bytes<uint16_t>(seg), [&] { sn::wide::sangnom_wide_row_sweep<uint16_t, 1024, 1, true>(&t, g, seg); });
         else
-            emul::run_cluster(0, G, threads, sn::wide::smem_bytes<float>(seg), [&] { sn::wide::sangnom_wide_row_sweep<float, 1024, 1>(&t, g, seg); });
+            emul::run_cluster(0, G, threads, sn::wide::smem_bytes<float>(seg), [&] { sn::wide::sangnom_wide_row_sweep<float, 1024, 1, true>(&t, g, seg); });
     }
     return 0;
 }

@@ -25,33 +25,42 @@ def emul():
     subprocess.run(["make", "-f", os.path.join(HERE, "emul", "Makefile")], check=True, stdout=subprocess.DEVNULL)
     L = C.CDLL(EMUL)
     L.emul_frame.restype = C.c_int
-    L.emul_frame.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.POINTER(C.c_int),
+    L.emul_frame.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.POINTER(C.c_void_p),
+                             C.POINTER(C.c_longlong), C.POINTER(C.c_int),
                              C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int]
     return L
 
 
-def emulate(L, planes, bits, order=1, aa=48, aac=0, dh=False, luma=True, chroma=True, parity=True, cluster=1):
-    """Frame-level host logic in numpy (field placement, plane skipping), plane passes through the emulated kernel."""
+def emulate(L, planes, bits, order=1, aa=48, aac=0, dh=False, luma=True, chroma=True, parity=True, cluster=1, out_of_place=False):
+    """Frame-level host logic in numpy (field placement, plane skipping), plane passes through the emulated kernel.
+    out_of_place: the kept rows are handed to the kernel as a separate packed field buffer (what the host path
+    uploads) and the kernel writes them into the dst plane itself."""
     off = cuda.resolve_offset(order, parity)
     sb = planes[0].dtype.itemsize
-    outs, proc = [], []
+    outs, proc, fields = [], [], {}
     for p, a in enumerate(planes[:3]):
         enabled = dh or (luma if p == 0 else chroma)
         if dh:
             d = np.full((a.shape[0] * 2, a.shape[1]), 0xEE, dtype=a.dtype)
-            d[off::2] = a
+            kept = a
         elif enabled:
             d = np.full_like(a, 0xEE)
-            d[off::2] = a[off::2]
+            kept = a[off::2]
         else:
             d = a.copy()
-        outs.append(d)
         if enabled:
+            if out_of_place:
+                fields[p] = np.ascontiguousarray(kept)
+            else:
+                d[off::2] = kept
             proc.append(p)
+        outs.append(d)
     n = len(proc)
     if n:
+        srcs = (C.c_void_p * n)(*[fields[p].ctypes.data if out_of_place else None for p in proc])
+        spitch = (C.c_longlong * n)(*[fields[p].strides[0] if out_of_place else 0 for p in proc])
         rc = L.emul_frame(sb, n, (C.c_void_p * n)(*[outs[p].ctypes.data for p in proc]),
-                          (C.c_longlong * n)(*[outs[p].strides[0] for p in proc]), (C.c_int * n)(*[outs[p].shape[1] for p in proc]),
+                          (C.c_longlong * n)(*[outs[p].strides[0] for p in proc]), srcs, spitch, (C.c_int * n)(*[outs[p].shape[1] for p in proc]),
                           (C.c_int * n)(*[outs[p].shape[0] for p in proc]), (C.c_int * n)(*[off] * n),
                           (C.c_float * n)(*[cuda.threshold(aa if p == 0 else aac, bits, sb) for p in proc]),
                           outs[0].shape[1], outs[0].shape[0], cluster)
@@ -86,7 +95,7 @@ def test_emulated_kernel_matches_oracle(emul, fmtname, w, h, kw, kind):
     fmt = FORMATS[fmtname]
     for i in range(2):
         fr = make_frame(31, w, h, fmt, kind, i)
-        got = emulate(emul, fr, fmt.bits, parity=(i == 0), **kw)
+        got = emulate(emul, fr, fmt.bits, parity=(i == 0), out_of_place=(i == 1), **kw)
         exp = O.oracle_frame(fr, fmt.bits, parity=(i == 0), **kw)
         assert_planes_equal(got, exp[:3], f"{fmtname} {w}x{h} {kw} frame {i}")
 
