@@ -248,7 +248,7 @@ int launch_passes(sn_ctx* ctx, const std::vector<std::vector<sn::PlaneTask>>& by
     size_t pos = 0;
     for (auto& v : by_pass) {
         if (v.empty()) continue;
-        SN_CUDA(ctx, sn::launch_plane_tasks(ctx->sample_bytes, dev_tasks + pos, (int)v.size(), sn::LaunchGeometry{ ctx->S, ctx->Hb }, stream));
+        SN_CUDA(ctx, sn::launch_plane_tasks(ctx->sample_bytes, dev_tasks + pos, (int)v.size(), sn::make_geometry(ctx->S, ctx->Hb), stream));
         ctx->stats.kernel_launches += 1;
         ctx->stats.planes_processed += v.size();
         pos += v.size();

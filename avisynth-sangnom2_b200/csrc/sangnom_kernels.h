@@ -42,7 +42,10 @@ struct PlaneTask {
 struct LaunchGeometry {
     int S;                  // pool row length in samples (align32 of the output luma width)
     int Hb;                 // pool rows: (output luma height + 1) >> 1
+    unsigned key_mask;      // 0x0FF00FF0 (8-bit kernel): passed as data so that it lives in a register, which lets
+                            // (sum & mask) | rank compile to one LOP3; make_geometry() fills it
 };
+inline LaunchGeometry make_geometry(int S, int Hb) { return LaunchGeometry{ S, Hb, 0x0FF00FF0u }; }
 
 // Widest pool each sample type can run (columns per thread x max threads per block).
 int max_pool_width(int sample_bytes);

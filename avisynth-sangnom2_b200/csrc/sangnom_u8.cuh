@@ -1,21 +1,29 @@
-// 8-bit flavour of the fused row sweep, written for the ALU-issue roof (DESIGN.md "Roofline"):
-// all cost arithmetic runs two pixels per 32-bit op in packed 16-bit lanes (u8 sums stay below
-// 5355, so plain 32-bit adds never carry across lanes), |a-b| on pixels runs four per op
-// (VABSDIFF4), the min over the nine costs and its tie-break are one VIMNMX3.U16x2 chain over
-// (cost<<4 | rank) keys with the aa threshold folded in as a tenth key, and the interpolation
-// operands are picked by a bitwise mux tree instead of branches.
+// 8-bit flavour of the fused row sweep, written for the instruction-issue roof.
 //
-// One thread owns 8 adjacent pool columns. Per pool row the block exchanges the vertical sums L
-// through a double-buffered shared row (one __syncthreads per row); the running term
-// M = B[r-1] + P[r] is the only state carried in registers (36 per thread).
+// One thread owns 8 adjacent pool columns. Per pool row r:
+//   phase A  kept row K[r+1] arrives in a shared-memory ring (bulk async copy, sangnom_stage.cuh); the thread
+//            takes its 16-byte window, builds the +-3 byte shifts, the 3-tap values of the row (once per
+//            row, reused for two pairs), the nine raw costs P[r+1] four pixels per VABSDIFF4, widens them
+//            to 16-bit lanes and publishes L = B[r-1] + P[r] + P[r+1] to a double-buffered shared row;
+//   barrier  one per row (block barrier, or the cluster barrier when the plane is split over blocks);
+//   phase B  per cost: 7-tap sum of L two columns per op, key = (sum & 0x0FF0) | rank in both lanes
+//            ((B << 4) | tie-break rank; B = wrap8(sum >> 4)), running term M = P[r+1] + (key >> 4) in ONE
+//            LEA.HI - the rank nibble of the upper lane that this shifts into the lower lane is a per-cost
+//            constant and is taken out again by the immediate of the next row's IADD3 - and a
+//            VIMNMX3.U16x2 chain over the keys with the aa threshold as a tenth key; then the interpolated
+//            picture row between K[r-1] and K[r] through a bitwise mux tree.
+// State carried in registers: M (36), the windows of three kept rows (12), their 3-tap bytes (12).
 //
-// Reference semantics: /root/reference/src/SangNom2.cpp :60-65 (3-tap), :108-117 (costs),
-// :138-152 (recursive blur, /16, wrap to u8), :208-249 (min, threshold, tie order, rounding mean).
+// Reference semantics: /root/reference/src/SangNom2.cpp :25-34 (edge replication), :60-65 (3-tap),
+// :108-117 (costs), :138-152 (recursive cost sum, /16, wrap to u8), :208-249 (min, threshold, tie order,
+// rounding mean), GetFrame :361-391 (kept field, border row).
 #pragma once
 #include "sangnom_cluster.cuh"
 #include "sangnom_kernels.h"
+#include "sangnom_stage.cuh"
 
 #include <cstdint>
+#include <type_traits>
 
 #ifndef SN_DYNAMIC_SMEM
 #define SN_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
@@ -26,19 +34,24 @@ namespace u8k {
 
 constexpr int kCols = 8;           // pool columns per thread
 constexpr int kLPad = 8;           // u16 elements of padding on each side of a shared L row (16 B)
+constexpr int kRing = 4;           // kept-row ring slots
+constexpr int kAhead = 3;          // rows staged ahead of the row being consumed
+constexpr int kRingPad = 16;       // bytes of halo on each side of a staged row segment
 
-// rank of cost buffer i in the reference's tie order (4,5,3,6,2,7,1,8,0), in both 16-bit lanes
-__device__ __forceinline__ constexpr uint32_t rank2(int i)
+// rank of cost buffer i in the reference's tie order (4,5,3,6,2,7,1,8,0)
+__device__ __forceinline__ constexpr uint32_t rank1(int i)
 {
     constexpr int r[kNumCost] = { 8, 6, 4, 2, 0, 1, 3, 5, 7 };
-    return (uint32_t)r[i] * 0x00010001u;
+    return (uint32_t)r[i];
 }
+__device__ __forceinline__ constexpr uint32_t rank2(int i) { return rank1(i) * 0x00010001u; }   // in both 16-bit lanes
+// what (key >> 4) leaks from the upper lane's rank nibble into the lower lane
+__device__ __forceinline__ constexpr uint32_t leak(int i) { return rank1(i) << 12; }
 
 __device__ __forceinline__ uint32_t fsr(uint32_t lo, uint32_t hi, int bytes) { return __funnelshift_r(lo, hi, bytes * 8); }
 __device__ __forceinline__ uint32_t lanes_lo(uint32_t w) { return __byte_perm(w, 0, 0x4140); }   // bytes 0,1 -> two u16 lanes
 __device__ __forceinline__ uint32_t lanes_hi(uint32_t w) { return __byte_perm(w, 0, 0x4342); }   // bytes 2,3 -> two u16 lanes
 __device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x6420); }   // low bytes of 4 lanes
-__device__ __forceinline__ uint32_t absdiff2(uint32_t a, uint32_t b) { return __vmaxu2(a, b) - __vminu2(a, b); }
 __device__ __forceinline__ uint32_t mean4(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) & 0xFEFEFEFEu) >> 1); }   // (a+b+1)>>1 per byte
 __device__ __forceinline__ uint32_t mux(uint32_t m, uint32_t a, uint32_t b) { return (a & ~m) | (b & m); }
 // 0xFF in every byte whose bit `bit` is set: PRMT's sign-replicate selectors (8|byte index). __byte_perm
@@ -79,43 +92,70 @@ struct Taps {
     }
 };
 
-// The two 3-tap values of one row for two pixels: f = T(m1,c,p1), b = T(p1,c,m1),
-// T(a,c,d) = wrap8((4a + 5c - d) >> 3). The +2048 bias keeps every lane positive through the
-// arithmetic shift and is a multiple of 256 after it, so it vanishes in the wrap.
-__device__ __forceinline__ void tap3_pair(uint32_t m1, uint32_t c, uint32_t p1, uint32_t& f, uint32_t& b)
+// The two 3-tap values of every pixel of one kept row, as bytes: f = T(x-1, x, x+1), b = T(x+1, x, x-1),
+// T(a,c,d) = wrap8((4a + 5c - d) >> 3). Computed once per row: as the upper row of a pair it supplies
+// (f1, b1) = (f, b), as the lower row (f2, b2) = (b, f) (reference :103-106).
+struct Tap3 { uint32_t f[2], b[2]; };
+
+__device__ __forceinline__ void tap3_row(const Taps& t, Tap3& o)
 {
-    const uint32_t u = c * 5u + 0x08000800u;
-    f = (((m1 << 2) + u - p1) >> 3) & 0x00FF00FFu;
-    b = (((p1 << 2) + u - m1) >> 3) & 0x00FF00FFu;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t m = t.at(-1, h), c = t.at(0, h), p = t.at(1, h);
+        uint32_t fl[2], bl[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint32_t m2 = q ? lanes_hi(m) : lanes_lo(m), c2 = q ? lanes_hi(c) : lanes_lo(c), p2 = q ? lanes_hi(p) : lanes_lo(p);
+            // the +2048 bias keeps every lane positive through the shift and is a multiple of 256 after it,
+            // so it vanishes in the wrap; the bits the 32-bit shift drags across lanes stay above bit 12
+            const uint32_t u = c2 * 5u + 0x08000800u;
+            fl[q] = ((m2 << 2) + u - p2) >> 3;
+            bl[q] = ((p2 << 2) + u - m2) >> 3;
+        }
+        o.f[h] = pack4(fl[0], fl[1]);
+        o.b[h] = pack4(bl[0], bl[1]);
+    }
 }
 
-struct RowState {
-    // 3-tap values of the pair (cur,next) kept for the interpolation one row later, as bytes
-    uint32_t f1[2], f2[2], b1[2], b2[2];
-};
-
-// Window of bytes x0-4 .. x0+11 of a picture row with the reference's edge replication
-// (loadPixel, SangNom2.cpp:25-34). vec: the row may be read with aligned 8/4-byte loads.
-__device__ __forceinline__ void load_window(const uint8_t* __restrict__ row, int x0, int W, bool vec, uint32_t (&w)[4])
+// Nine raw costs of the pair (upper row c, lower row n) for 8 pixels, as bytes (two words per cost).
+__device__ __forceinline__ void pair_costs(const Taps& c, const Tap3& c3, const Taps& n, const Tap3& n3, uint32_t (&P)[kNumCost][2])
 {
-    if (x0 >= W) { w[0] = w[1] = w[2] = w[3] = 0; return; }
-    if (vec) {
-        const uint2 own = *reinterpret_cast<const uint2*>(row + x0);
-        w[1] = own.x; w[2] = own.y;
-        w[0] = x0 > 0 ? *reinterpret_cast<const uint32_t*>(row + x0 - 4) : 0u;
-        w[3] = x0 + 8 < W ? *reinterpret_cast<const uint32_t*>(row + x0 + 8) : 0u;
-    } else {
+    const int tap_of[kNumCost] = { -3, -2, -1, 0, 0, 0, 1, 2, 3 };
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            uint32_t v = 0;
+    for (int i = 0; i < kNumCost; ++i) {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int x = x0 - 4 + 4 * i + b;
-                if (x >= 0 && x < W) v |= (uint32_t)row[x] << (8 * b);
-            }
-            w[i] = v;
+        for (int h = 0; h < 2; ++h) {
+            if (i == 3) P[i][h] = __vabsdiffu4(c3.f[h], n3.b[h]);          // |f1 - f2|
+            else if (i == 5) P[i][h] = __vabsdiffu4(c3.b[h], n3.f[h]);     // |b1 - b2|
+            else P[i][h] = __vabsdiffu4(c.at(tap_of[i], h), n.at(-tap_of[i], h));
         }
     }
+}
+
+// Interpolated pixels (8 bytes) of the row between `c` and `n` from the four min-key words.
+__device__ __forceinline__ uint2 interpolate8(const Taps& c, const Tap3& c3, const Taps& n, const Tap3& n3, const uint32_t (&kmin)[4])
+{
+    uint2 out;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t ranks = pack4(kmin[2 * h], kmin[2 * h + 1]);     // low nibble of each byte = winning rank
+        const uint32_t m0 = byte_mask_from_bit(ranks, 0), m1 = byte_mask_from_bit(ranks, 1);
+        const uint32_t m2 = byte_mask_from_bit(ranks, 2), m3 = byte_mask_from_bit(ranks, 3);
+        // operands by rank: 0 (c0,n0) 1 (b1,b2) 2 (f1,f2) 3 (c+1,n-1) 4 (c-1,n+1) 5 (c+2,n-2) 6 (c-2,n+2) 7 (c+3,n-3) 8 (c-3,n+3)
+        const uint32_t a01 = mux(m0, c.at(0, h), c3.b[h]), a23 = mux(m0, c3.f[h], c.at(1, h));
+        const uint32_t a45 = mux(m0, c.at(-1, h), c.at(2, h)), a67 = mux(m0, c.at(-2, h), c.at(3, h));
+        const uint32_t a = mux(m3, mux(m2, mux(m1, a01, a23), mux(m1, a45, a67)), c.at(-3, h));
+        const uint32_t b01 = mux(m0, n.at(0, h), n3.f[h]), b23 = mux(m0, n3.b[h], n.at(-1, h));
+        const uint32_t b45 = mux(m0, n.at(1, h), n.at(-2, h)), b67 = mux(m0, n.at(2, h), n.at(-3, h));
+        const uint32_t b = mux(m3, mux(m2, mux(m1, b01, b23), mux(m1, b45, b67)), n.at(3, h));
+        (h ? out.y : out.x) = mean4(a, b);
+    }
+    return out;
+}
+
+// Replicate the picture edges inside a window of bytes x0-4 .. x0+11 (reference loadPixel :25-34).
+__device__ __forceinline__ void fix_edges(uint32_t (&w)[4], int x0, int W)
+{
     if (x0 == 0) w[0] = (w[1] & 0xFFu) * 0x01010101u;
     if (x0 + 11 > W - 1) {                       // right edge inside this window: replicate pixel W-1
         const int e = W - 1 - (x0 - 4);          // window byte index of the last picture pixel (>= 4)
@@ -132,87 +172,49 @@ __device__ __forceinline__ void load_window(const uint8_t* __restrict__ row, int
     }
 }
 
-// Eight stale cost bytes of buffer i at pool row r, columns x0..x0+7 (0 outside the handed-over regions).
-__device__ __forceinline__ uint2 state_load8(const CostState& s, int i, int r, int x0, int S)
+// Where the cost state of one pool row lives for this thread's 8 columns: bytes of buffer i at p + i * stride.
+// p == nullptr: outside the handed-over regions (reads as the zero-filled pool, nothing to write).
+struct StateRow { uint8_t* p; size_t stride; };
+
+__device__ __forceinline__ StateRow state_row(const CostState& s, int r, int x0, int S)
 {
     if (s.b != nullptr && r >= s.b_r0 && r <= s.b_r1) {
         const int nb = s.b_r1 - s.b_r0 + 1;
-        return __ldg(reinterpret_cast<const uint2*>(static_cast<const uint8_t*>(s.b) + ((size_t)i * nb + (r - s.b_r0)) * S + x0));
+        return StateRow{ static_cast<uint8_t*>(s.b) + (size_t)(r - s.b_r0) * S + x0, (size_t)nb * S };
     }
     if (s.a != nullptr && x0 >= s.a_x0 && r >= 1 && r <= s.a_rows) {
         const int wa = S - s.a_x0;
-        return __ldg(reinterpret_cast<const uint2*>(static_cast<const uint8_t*>(s.a) + ((size_t)i * (s.a_rows + 1) + r) * wa + (x0 - s.a_x0)));
+        return StateRow{ static_cast<uint8_t*>(s.a) + (size_t)r * wa + (x0 - s.a_x0), (size_t)(s.a_rows + 1) * wa };
     }
-    return make_uint2(0u, 0u);
+    return StateRow{ nullptr, 0 };
 }
 
-__device__ __forceinline__ void state_store8(const CostState& s, int i, int r, int x0, int S, uint2 v)
+// 8 bytes at row positions p0 .. p0+7 with zero outside [0, W); `fast`: 8-byte aligned loads are legal
+__device__ __forceinline__ uint2 load8_guarded(const uint8_t* __restrict__ row, int p0, int W, bool fast)
 {
-    if (s.b != nullptr && r >= s.b_r0 && r <= s.b_r1) {
-        const int nb = s.b_r1 - s.b_r0 + 1;
-        *reinterpret_cast<uint2*>(static_cast<uint8_t*>(s.b) + ((size_t)i * nb + (r - s.b_r0)) * S + x0) = v;
-    } else if (s.a != nullptr && x0 >= s.a_x0 && r >= 1 && r <= s.a_rows) {
-        const int wa = S - s.a_x0;
-        *reinterpret_cast<uint2*>(static_cast<uint8_t*>(s.a) + ((size_t)i * (s.a_rows + 1) + r) * wa + (x0 - s.a_x0)) = v;
+    if (fast && p0 >= 0 && p0 + 8 <= W) return *reinterpret_cast<const uint2*>(row + p0);
+    uint2 v = make_uint2(0u, 0u);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const int p = p0 + b;
+        if (p >= 0 && p < W) { const uint32_t px = (uint32_t)row[p] << (8 * (b & 3)); if (b < 4) v.x |= px; else v.y |= px; }
     }
+    return v;
 }
 
-// Raw costs P of one row pair for this thread's 8 pixels, as nine sets of four packed-lane words,
-// plus the 3-tap values the interpolation of this pair will need.
-__device__ __forceinline__ void pair_costs(const Taps& c, const Taps& n, uint32_t (&P)[kNumCost][4], RowState& keep)
+// Shared memory of one block (seg_cols pool columns, T = seg_cols / 8 threads):
+//   L     [2 parities][9 costs][2 halves][T + 2] uint2   vertical sums as 16-bit lanes: half 0 = columns 0..3 of
+//         every thread, half 1 = columns 4..7 (entry -1 / T: the neighbour segment's edge or the clamp). A thread
+//         reads half1[t-1], half0[t], half1[t], half0[t+1]: consecutive lanes touch consecutive 8-byte words.
+//   ring  [kRing][ring_stride]  staged kept rows, row position p at offset p - seg_x0 + kRingPad
+//   mbar  [kRing]               one mbarrier per ring slot
+//   task                        this block's PlaneTask
+inline __host__ __device__ int ring_stride(int seg_cols) { return (seg_cols + 2 * kRingPad + 15) & ~15; }
+inline __host__ __device__ int l_half_stride(int seg_cols) { return seg_cols / kCols + 2; }                  // uint2 entries
+inline size_t smem_bytes(int seg_cols)
 {
-    // seven pixel-pair costs, four pixels per VABSDIFF4, then widened to 16-bit lanes
-    const int tap_of[kNumCost] = { -3, -2, -1, 0, 0, 0, 1, 2, 3 };
-#pragma unroll
-    for (int i = 0; i < kNumCost; ++i) {
-        if (i == 3 || i == 5) continue;
-        const int k = tap_of[i];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const uint32_t d = __vabsdiffu4(c.at(k, h), n.at(-k, h));
-            P[i][2 * h] = lanes_lo(d);
-            P[i][2 * h + 1] = lanes_hi(d);
-        }
-    }
-    // the two 3-tap costs, two pixels per op
-    uint32_t f1[4], b1[4], f2[4], b2[4];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const uint32_t cm = c.at(-1, h), cc = c.at(0, h), cp = c.at(1, h);
-        const uint32_t nm = n.at(-1, h), nc = n.at(0, h), np = n.at(1, h);
-        tap3_pair(lanes_lo(cm), lanes_lo(cc), lanes_lo(cp), f1[2 * h], b1[2 * h]);
-        tap3_pair(lanes_hi(cm), lanes_hi(cc), lanes_hi(cp), f1[2 * h + 1], b1[2 * h + 1]);
-        tap3_pair(lanes_lo(nm), lanes_lo(nc), lanes_lo(np), b2[2 * h], f2[2 * h]);      // next row: roles swap
-        tap3_pair(lanes_hi(nm), lanes_hi(nc), lanes_hi(np), b2[2 * h + 1], f2[2 * h + 1]);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { P[3][q] = absdiff2(f1[q], f2[q]); P[5][q] = absdiff2(b1[q], b2[q]); }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        keep.f1[h] = pack4(f1[2 * h], f1[2 * h + 1]); keep.f2[h] = pack4(f2[2 * h], f2[2 * h + 1]);
-        keep.b1[h] = pack4(b1[2 * h], b1[2 * h + 1]); keep.b2[h] = pack4(b2[2 * h], b2[2 * h + 1]);
-    }
-}
-
-// Interpolated pixels (8 bytes) of the row between `c` and `n` from the four min-key words.
-__device__ __forceinline__ uint2 interpolate8(const Taps& c, const Taps& n, const RowState& sg, const uint32_t (&kmin)[4])
-{
-    uint2 out;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const uint32_t ranks = pack4(kmin[2 * h], kmin[2 * h + 1]);     // low nibble of each byte = winning rank
-        const uint32_t m0 = byte_mask_from_bit(ranks, 0), m1 = byte_mask_from_bit(ranks, 1);
-        const uint32_t m2 = byte_mask_from_bit(ranks, 2), m3 = byte_mask_from_bit(ranks, 3);
-        // operands by rank: 0 (c0,n0) 1 (b1,b2) 2 (f1,f2) 3 (c+1,n-1) 4 (c-1,n+1) 5 (c+2,n-2) 6 (c-2,n+2) 7 (c+3,n-3) 8 (c-3,n+3)
-        const uint32_t a01 = mux(m0, c.at(0, h), sg.b1[h]), a23 = mux(m0, sg.f1[h], c.at(1, h));
-        const uint32_t a45 = mux(m0, c.at(-1, h), c.at(2, h)), a67 = mux(m0, c.at(-2, h), c.at(3, h));
-        const uint32_t a = mux(m3, mux(m2, mux(m1, a01, a23), mux(m1, a45, a67)), c.at(-3, h));
-        const uint32_t b01 = mux(m0, n.at(0, h), sg.b2[h]), b23 = mux(m0, sg.f2[h], n.at(-1, h));
-        const uint32_t b45 = mux(m0, n.at(1, h), n.at(-2, h)), b67 = mux(m0, n.at(2, h), n.at(-3, h));
-        const uint32_t b = mux(m3, mux(m2, mux(m1, b01, b23), mux(m1, b45, b67)), n.at(3, h));
-        (h ? out.y : out.x) = mean4(a, b);
-    }
-    return out;
+    return (size_t)2 * kNumCost * 2 * l_half_stride(seg_cols) * sizeof(uint2) + (size_t)kRing * ring_stride(seg_cols) + kRing * sizeof(stage::Mbar) +
+           ((sizeof(PlaneTask) + 15) & ~(size_t)15);
 }
 
 template <int kMaxThreads, int kMinBlocks, bool kClustered>
@@ -223,170 +225,278 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     // a plane wider than one block is split into column segments over the blocks of a cluster
     const unsigned G = kClustered ? cl::size() : 1u;      // kClustered = false: one block per plane, no cluster code at all
     const unsigned crank = kClustered ? cl::rank() : 0u;
-    const PlaneTask t = tasks[blockIdx.x / G];
     const int S = g.S;
-    const int LS = seg_cols + 2 * kLPad;                            // u16 elements per shared L row of this segment
-    uint16_t* const Lbase = reinterpret_cast<uint16_t*>(smem_raw);  // [2][9][LS]
+    const uint32_t keymask = g.key_mask;                            // 0x0FF00FF0, kept in a register so (sum & mask) | rank is one LOP3
+    const int HS = l_half_stride(seg_cols);
+    uint2* const Lbase = reinterpret_cast<uint2*>(smem_raw);
+    const int rstride = ring_stride(seg_cols);
+    uint8_t* const ring = smem_raw + (size_t)2 * kNumCost * 2 * HS * sizeof(uint2);
+    stage::Mbar* const mbar = reinterpret_cast<stage::Mbar*>(ring + (size_t)kRing * rstride);
+    // the task lives in shared memory: its rarely used fields (cost-state regions, pitches) are re-read where needed
+    // instead of occupying registers for the whole sweep
+    {
+        uint32_t* const dst = reinterpret_cast<uint32_t*>(mbar + kRing);
+        const uint32_t* const from = reinterpret_cast<const uint32_t*>(tasks + blockIdx.x / G);
+        for (unsigned k = threadIdx.x; k < sizeof(PlaneTask) / 4; k += blockDim.x) dst[k] = from[k];
+        __syncthreads();
+    }
+    const PlaneTask& t = *reinterpret_cast<const PlaneTask*>(mbar + kRing);
 
     const int W = t.width, n = t.kept_rows, R = t.sweep_rows;
-    const int lx = threadIdx.x * kCols;                             // column inside the segment
-    const int x0 = (int)crank * seg_cols + lx;                      // pool column
+    const int tid = (int)threadIdx.x, T = seg_cols / kCols;
+    const int lx = tid * kCols;                                     // column inside the segment
+    const int seg_x0 = (int)crank * seg_cols;
+    const int x0 = seg_x0 + lx;                                     // pool column
     const bool plane_first = x0 == 0, plane_last = x0 + kCols == S;
-    const bool seg_first = lx == 0, seg_last = lx + kCols == seg_cols;
-    uint8_t* const plane = static_cast<uint8_t*>(t.plane);
+    const bool seg_first = tid == 0, seg_last = tid == T - 1;
     const uint8_t* const src = static_cast<const uint8_t*>(t.src);
-    const long long pitch = t.pitch, src_pitch = t.src_pitch;
-    const long long wpad = ((long long)W + 15) & ~15LL;
-    const bool vec = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)src_pitch) & 15) == 0 && src_pitch >= wpad;      // aligned vector loads of kept rows
-    const bool vec_out = ((reinterpret_cast<uintptr_t>(plane) | (uintptr_t)pitch) & 15) == 0 && pitch >= wpad;        // aligned vector stores
+    const long long src_pitch = t.src_pitch;
+    const int wpad = (W + 15) & ~15;
     // which of my 8 columns carry pixels: all, none, or a prefix (the one thread that straddles W)
     const int npix = min(max(W - x0, 0), kCols);
-    const uint32_t pixmask_lo = npix >= 4 ? 0xFFFFFFFFu : (npix <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - npix))));
-    const uint32_t pixmask_hi = npix >= 8 ? 0xFFFFFFFFu : (npix <= 4 ? 0u : (0xFFFFFFFFu >> (8 * (8 - npix))));
+    const bool edge = npix > 0 && (x0 == 0 || x0 + 11 > W - 1);
 
+    // ---- staging of kept rows: positions [lo, hi) of every kept row go to ring offset (position - seg_x0 + 16) ----
+    const int lo = max(seg_x0 - kRingPad, 0), hi = min(seg_x0 + seg_cols + kRingPad, wpad);
+    const bool seg_has_pixels = seg_x0 < W;
+    // bulk copies need 16-byte aligned rows and may read up to wpad bytes of a row
+    const bool bulk = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)src_pitch | (uintptr_t)seg_cols) & 15) == 0 && src_pitch >= wpad;
+    const bool fast8 = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)src_pitch) & 7) == 0;
     auto kept_row = [&](int j) -> const uint8_t* { return src + (long long)j * src_pitch; };
-    auto store8 = [&](uint8_t* row, uint2 v) {
+    auto slot_of = [&](int j) -> uint8_t* { return ring + (size_t)(j & (kRing - 1)) * rstride; };
+    // bulk mode: thread 0 starts the copy of kept row j
+    auto issue_row = [&](int j) {
+        stage::bulk_load(slot_of(j) + (lo - seg_x0 + kRingPad), kept_row(j) + lo, (unsigned)(hi - lo), &mbar[j & (kRing - 1)]);
+    };
+    // cooperative mode (unaligned sources): my own 8 bytes of a row, edge threads also the neighbour segments' halo
+    auto coop_load = [&](int j, uint2 (&v)[3]) {
+        const uint8_t* row = kept_row(j);
+        v[0] = load8_guarded(row, x0, W, fast8);
+        if (kClustered && seg_first) v[1] = load8_guarded(row, x0 - 8, W, fast8);
+        if (kClustered && seg_last) v[2] = load8_guarded(row, x0 + 8, W, fast8);
+    };
+    auto coop_store = [&](int j, const uint2 (&v)[3]) {
+        uint8_t* s = slot_of(j) + kRingPad + lx;
+        *reinterpret_cast<uint2*>(s) = v[0];
+        if (kClustered && seg_first) *reinterpret_cast<uint2*>(s - 8) = v[1];
+        if (kClustered && seg_last) *reinterpret_cast<uint2*>(s + 8) = v[2];
+    };
+    // my window of kept row j (bytes x0-4 .. x0+11) out of the ring, picture edges replicated
+    auto take_window = [&](int j, uint32_t (&w)[4]) {
+        if (bulk) stage::mbar_wait(&mbar[j & (kRing - 1)], (unsigned)(j / kRing) & 1u);
+        const uint8_t* s = slot_of(j) + kRingPad + lx;
+        w[0] = *reinterpret_cast<const uint32_t*>(s - 4);
+        const uint2 own = *reinterpret_cast<const uint2*>(s);
+        w[1] = own.x; w[2] = own.y;
+        w[3] = *reinterpret_cast<const uint32_t*>(s + 8);
+        if (edge) fix_edges(w, x0, W);
+    };
+    // my 8 bytes of a picture row of the dst plane
+    auto store8 = [&](int y, uint2 v) {
+        uint8_t* const row = static_cast<uint8_t*>(t.plane) + (long long)y * t.pitch;
+        const bool vec_out = ((reinterpret_cast<uintptr_t>(t.plane) | (uintptr_t)t.pitch) & 7) == 0;
         if (npix == kCols && vec_out) { *reinterpret_cast<uint2*>(row + x0) = v; return; }
 #pragma unroll
         for (int b = 0; b < 8; ++b) if (b < npix) row[x0 + b] = (uint8_t)(((b < 4 ? v.x : v.y) >> (8 * (b & 3))) & 0xFFu);
     };
 
-    // ---- border row without a neighbour pair (reference GetFrame :380-391) ----
-    if (npix > 0) {
-        uint8_t* to = t.offset == 0 ? plane + (long long)(t.height - 1) * pitch : plane;
-        uint32_t w[4];
-        load_window(kept_row(t.offset == 0 ? n - 1 : 0), x0, W, vec, w);
-        store8(to, make_uint2(w[1], w[2]));
-        if (t.copy_kept) {                       // last kept row; rows 0..n-2 are written as the sweep passes them
-            if (t.offset != 0) load_window(kept_row(n - 1), x0, W, vec, w);
-            store8(plane + (long long)(t.offset + 2 * (n - 1)) * pitch, make_uint2(w[1], w[2]));
+    uint2 pre[3] = {};                                  // cooperative mode: the row that goes into the ring next iteration
+    if (seg_has_pixels) {
+        if (bulk) {
+            if (tid == 0) {
+#pragma unroll
+                for (int s = 0; s < kRing; ++s) stage::mbar_init(&mbar[s], 1);
+                stage::fence_mbar_init();
+            }
+            __syncthreads();
+            if (tid == 0)
+                for (int j = 0; j <= kAhead && j < n; ++j) issue_row(j);
+        } else {
+            for (int j = 0; j < kAhead && j < n; ++j) { coop_load(j, pre); coop_store(j, pre); }
+            if (kAhead < n) coop_load(kAhead, pre);
+            __syncthreads();
         }
     }
 
-    // ---- running term M = B[r-1] + P[r]; B[0] = 0 so M starts as P[1] ----
+    // ---- running term M = B[r-1] + P[r] (+ leak); B[0] = 0 so M starts as P[1] ----
     uint32_t M[kNumCost][4];
-    uint32_t wa[4], wb[4], wc[4], wpre[4];          // windows of K[r-1], K[r], K[r+1], K[r+2]
-    RowState sg_prev{}, sg_next{};                   // 3-tap bytes of pairs (r-1,r) and (r,r+1)
+    uint32_t wa[4] = {}, wb[4] = {}, wc[4] = {};      // windows of K[r-1], K[r], K[r+1]
+    Tap3 ta{}, tb{}, tc{};                             // their 3-tap bytes
 
-    // Raw cost row `row` (pool row index) into P: from pixels where this thread has them and the
-    // pair exists, otherwise from the cost state the previous pass of the frame left.
-    auto cost_row = [&](int row, const uint32_t (&cw)[4], const uint32_t (&nw)[4], uint32_t (&P)[kNumCost][4], RowState& keep) {
-        const bool pair = row <= n - 1;              // pool row j+1 holds the costs of pair (K[j], K[j+1])
-        if (pair && npix == kCols) {
-            Taps c, nx;
-            c.build(cw); nx.build(nw);
-            pair_costs(c, nx, P, keep);
-            return;
+    // Stale costs of pool row `row` for my columns: what the previous pass of the frame left there.
+    auto stale_costs = [&](int row, uint32_t (&Pb)[kNumCost][2]) {
+        const StateRow in = state_row(t.in, row, x0, S);
+#pragma unroll
+        for (int i = 0; i < kNumCost; ++i) {
+            const uint2 v = in.p != nullptr ? __ldg(reinterpret_cast<const uint2*>(in.p + i * in.stride)) : make_uint2(0u, 0u);
+            Pb[i][0] = v.x; Pb[i][1] = v.y;
         }
-        uint2 st[kNumCost];
-#pragma unroll
-        for (int i = 0; i < kNumCost; ++i) st[i] = state_load8(t.in, i, row, x0, S);
-        if (pair && npix > 0) {                      // the straddling thread: pixels left, stale right
-            Taps c, nx;
-            c.build(cw); nx.build(nw);
-            pair_costs(c, nx, P, keep);
-#pragma unroll
-            for (int i = 0; i < kNumCost; ++i) {
-                const uint32_t lo = (pack4(P[i][0], P[i][1]) & pixmask_lo) | (st[i].x & ~pixmask_lo);
-                const uint32_t hi = (pack4(P[i][2], P[i][3]) & pixmask_hi) | (st[i].y & ~pixmask_hi);
-                P[i][0] = lanes_lo(lo); P[i][1] = lanes_hi(lo); P[i][2] = lanes_lo(hi); P[i][3] = lanes_hi(hi);
-            }
+    };
+    // Raw cost row `row` (pool row index = pair (K[row-1], K[row])) as bytes. kFull: this thread has 8 pixel columns.
+    auto cost_bytes = [&](auto full, int row, const Taps& c, const Tap3& c3, const Taps& nx, const Tap3& n3, uint32_t (&Pb)[kNumCost][2]) {
+        constexpr bool kFull = decltype(full)::value;
+        const bool pair = row <= n - 1;
+        if (kFull) {
+            if (pair) pair_costs(c, c3, nx, n3, Pb); else stale_costs(row, Pb);
         } else {
+            stale_costs(row, Pb);
+            if (pair && npix > 0) {                      // the straddling thread: pixels left, stale right
+                const uint32_t pixmask_lo = npix >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (4 - npix)));
+                const uint32_t pixmask_hi = npix <= 4 ? 0u : (0xFFFFFFFFu >> (8 * (8 - npix)));
+                uint32_t Px[kNumCost][2];
+                pair_costs(c, c3, nx, n3, Px);
 #pragma unroll
-            for (int i = 0; i < kNumCost; ++i) {
-                P[i][0] = lanes_lo(st[i].x); P[i][1] = lanes_hi(st[i].x); P[i][2] = lanes_lo(st[i].y); P[i][3] = lanes_hi(st[i].y);
+                for (int i = 0; i < kNumCost; ++i) {
+                    Pb[i][0] = (Px[i][0] & pixmask_lo) | (Pb[i][0] & ~pixmask_lo);
+                    Pb[i][1] = (Px[i][1] & pixmask_hi) | (Pb[i][1] & ~pixmask_hi);
+                }
             }
         }
     };
 
-    load_window(kept_row(0), x0, W, vec, wa);
-    if (n >= 2) load_window(kept_row(1), x0, W, vec, wb); else { wb[0] = wb[1] = wb[2] = wb[3] = 0; }
-    if (n >= 3) load_window(kept_row(2), x0, W, vec, wc); else { wc[0] = wc[1] = wc[2] = wc[3] = 0; }
-    cost_row(1, wa, wb, M, sg_next);
+    {
+        Taps Ta{}, Tb{};
+        if (npix > 0) {
+            take_window(0, wa);
+            Ta.build(wa);
+            tap3_row(Ta, ta);
+            if (n >= 2) { take_window(1, wb); Tb.build(wb); tap3_row(Tb, tb); }
+            // border row without a neighbour pair (reference GetFrame :380-391) and, for a one-pair-less plane, the kept row
+            if (t.offset != 0) store8(0, make_uint2(wa[1], wa[2]));
+            if (n == 1) {
+                if (t.offset == 0) store8(t.height - 1, make_uint2(wa[1], wa[2]));
+                if (t.copy_kept) store8(t.offset, make_uint2(wa[1], wa[2]));
+            }
+        }
+        uint32_t Pb[kNumCost][2];
+        if (npix == kCols) cost_bytes(std::true_type{}, 1, Ta, ta, Tb, tb, Pb);
+        else cost_bytes(std::false_type{}, 1, Ta, ta, Tb, tb, Pb);
+#pragma unroll
+        for (int i = 0; i < kNumCost; ++i) {
+            M[i][0] = lanes_lo(Pb[i][0]) + leak(i); M[i][1] = lanes_hi(Pb[i][0]) + leak(i);
+            M[i][2] = lanes_lo(Pb[i][1]) + leak(i); M[i][3] = lanes_hi(Pb[i][1]) + leak(i);
+        }
+    }
+    // every thread has left ring slot 0 before it is refilled; all blocks of a cluster run before the first DSMEM store
+    if constexpr (kClustered) cl::sync_all(); else __syncthreads();
 
     const uint32_t tkey = (uint32_t)min(t.thr_i + 1, 4095) * 0x00100010u;    // (thr+1) << 4 in both lanes
     const bool exporting = t.out.a != nullptr || t.out.b != nullptr;
 
-    for (int r = 1; r <= R; ++r) {
-        // wa = K[r-1], wb = K[r], wc = K[r+1]; start the loads of K[r+2]
-        if (r + 2 <= n - 1) load_window(kept_row(r + 2), x0, W, vec, wpre);
+    // The sweep. Instantiated twice: kFull for warps whose every thread owns 8 pixel columns (no stale-state or
+    // masking code on the hot path), general for warps that hold pad / stale columns. Both run the same barriers.
+    auto sweep = [&](auto full) {
+        constexpr bool kFull = decltype(full)::value;
+        for (int r = 1; r <= R; ++r) {
+            // wa = K[r-1], wb = K[r]; stage the ring, take K[r+1]
+            if (seg_has_pixels) {
+                if (bulk) {
+                    if (tid == 0 && r + kAhead < n) issue_row(r + kAhead);
+                } else {
+                    if (r + kAhead - 1 < n) coop_store(r + kAhead - 1, pre);
+                    if (r + kAhead < n) coop_load(r + kAhead, pre);
+                }
+            }
+            Taps Tb{}, Tc{};
+            if (kFull || npix > 0) {
+                Tb.build(wb);
+                if (r + 1 <= n - 1) { take_window(r + 1, wc); Tc.build(wc); tap3_row(Tc, tc); }
+            }
 
-        // ---- P[r+1], L = M + P[r+1] -> shared row; M keeps P[r+1] until B[r] is known ----
-        sg_prev = sg_next;
-        uint16_t* const Lrow = Lbase + (size_t)(r & 1) * kNumCost * LS + kLPad;
-        {
-            uint32_t P[kNumCost][4];
-            cost_row(r + 1, wb, wc, P, sg_next);
+            // ---- P[r+1], L = M + P[r+1] -> shared row; M keeps P[r+1] until B[r] is known ----
+            uint2* const Lrow = Lbase + (size_t)(r & 1) * kNumCost * 2 * HS + 1 + tid;     // half 0 of cost 0, my entry
+            {
+                uint32_t Pb[kNumCost][2];
+                cost_bytes(full, r + 1, Tb, tb, Tc, tc, Pb);
+#pragma unroll
+                for (int i = 0; i < kNumCost; ++i) {
+                    const uint32_t P0 = lanes_lo(Pb[i][0]), P1 = lanes_hi(Pb[i][0]), P2 = lanes_lo(Pb[i][1]), P3 = lanes_hi(Pb[i][1]);
+                    const uint2 Lxy = make_uint2(M[i][0] + P0 - leak(i), M[i][1] + P1 - leak(i));
+                    const uint2 Lzw = make_uint2(M[i][2] + P2 - leak(i), M[i][3] + P3 - leak(i));
+                    uint2* const h0 = Lrow + (size_t)i * 2 * HS;
+                    uint2* const h1 = h0 + HS;
+                    *h0 = Lxy;
+                    *h1 = Lzw;
+                    if (seg_first) {
+                        if (plane_first) { const uint32_t e = (Lxy.x & 0xFFFFu) * 0x00010001u; h1[-1] = make_uint2(e, e); }      // clamp at column 0
+                        else {                                                       // my first columns are the left neighbour's right halo
+                            cl::store_remote(&h0[T].x, crank - 1, Lxy.x);
+                            cl::store_remote(&h0[T].y, crank - 1, Lxy.y);
+                        }
+                    }
+                    if (seg_last) {
+                        if (plane_last) { const uint32_t e = (Lzw.y >> 16) * 0x00010001u; h0[1] = make_uint2(e, e); }           // clamp at column S-1
+                        else {                                                       // my last columns are the right neighbour's left halo
+                            cl::store_remote(&h1[-T].x, crank + 1, Lzw.x);
+                            cl::store_remote(&h1[-T].y, crank + 1, Lzw.y);
+                        }
+                    }
+                    M[i][0] = P0; M[i][1] = P1; M[i][2] = P2; M[i][3] = P3;
+                }
+            }
+            if constexpr (kClustered) cl::sync_all(); else __syncthreads();
+
+            // ---- per cost: 7-tap sum, key = (B << 4) | rank, M = P[r+1] + B (+ leak), min over the keys ----
+            uint32_t kmin[4] = { tkey, tkey, tkey, tkey };
+            uint32_t held[4] = {};
+            const StateRow out = exporting ? state_row(t.out, r, x0, S) : StateRow{ nullptr, 0 };
 #pragma unroll
             for (int i = 0; i < kNumCost; ++i) {
-                uint4 L;
-                L.x = M[i][0] + P[i][0]; L.y = M[i][1] + P[i][1]; L.z = M[i][2] + P[i][2]; L.w = M[i][3] + P[i][3];
-                uint16_t* row = Lrow + i * LS;
-                *reinterpret_cast<uint4*>(row + lx) = L;
-                if (seg_first) {
-                    if (plane_first) { const uint32_t e = (L.x & 0xFFFFu) * 0x00010001u; *reinterpret_cast<uint2*>(row - 4) = make_uint2(e, e); }   // clamp at column 0
-                    else {                                                       // my first columns are the left neighbour's right halo
-                        cl::store_remote(reinterpret_cast<uint32_t*>(row + seg_cols), crank - 1, L.x);
-                        cl::store_remote(reinterpret_cast<uint32_t*>(row + seg_cols + 2), crank - 1, L.y);
-                    }
+                const uint2* const h0 = Lrow + (size_t)i * 2 * HS;
+                const uint2* const h1 = h0 + HS;
+                const uint2 lh = h1[-1];        // (l-4,l-3) (l-2,l-1)
+                const uint2 oa = h0[0];         // (l0,l1) (l2,l3)
+                const uint2 ob = h1[0];         // (l4,l5) (l6,l7)
+                const uint2 rh = h0[1];         // (l8,l9) (l10,l11)
+                const uint32_t Wm2 = lh.x, Wm1 = lh.y, W0 = oa.x, W1 = oa.y, W2 = ob.x, W3 = ob.y, W4 = rh.x, W5 = rh.y;
+                // Z_k = W[k-1]+W[k]+W[k+1] (even / odd triples), X_k = Z_k + W[k-2];
+                // H7_k = Z_k + (X_k.hi, X_{k+1}.lo)  -> lanes (sum l[2k-3..2k+3], sum l[2k-2..2k+4])
+                const uint32_t Z0 = Wm1 + W0 + W1, Z1 = W0 + W1 + W2, Z2 = W1 + W2 + W3, Z3 = W2 + W3 + W4, Z4 = W3 + W4 + W5;
+                const uint32_t X0 = Z0 + Wm2, X1 = Z1 + Wm1, X2 = Z2 + W0, X3 = Z3 + W1, X4 = Z4 + W2;
+                uint32_t key[4];
+                key[0] = ((Z0 + __funnelshift_r(X0, X1, 16)) & keymask) | rank2(i);
+                key[1] = ((Z1 + __funnelshift_r(X1, X2, 16)) & keymask) | rank2(i);
+                key[2] = ((Z2 + __funnelshift_r(X2, X3, 16)) & keymask) | rank2(i);
+                key[3] = ((Z3 + __funnelshift_r(X3, X4, 16)) & keymask) | rank2(i);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    M[i][q] += key[q] >> 4;                                     // LEA.HI: P[r+1] + B[r] + leak(i)
+                    if (i & 1) kmin[q] = __vimin3_u16x2(kmin[q], held[q], key[q]);
+                    else if (i == kNumCost - 1) kmin[q] = __vminu2(kmin[q], key[q]);
+                    else held[q] = key[q];
                 }
-                if (seg_last) {
-                    if (plane_last) { const uint32_t e = (L.w >> 16) * 0x00010001u; *reinterpret_cast<uint2*>(row + seg_cols) = make_uint2(e, e); }   // clamp at column S-1
-                    else {                                                       // my last columns are the right neighbour's left halo
-                        cl::store_remote(reinterpret_cast<uint32_t*>(row - 4), crank + 1, L.z);
-                        cl::store_remote(reinterpret_cast<uint32_t*>(row - 2), crank + 1, L.w);
-                    }
+                // hand the blurred row to the next pass of this frame
+                if (out.p != nullptr)
+                    *reinterpret_cast<uint2*>(out.p + i * out.stride) = make_uint2(pack4(key[0] >> 4, key[1] >> 4), pack4(key[2] >> 4, key[3] >> 4));
+            }
+
+            // ---- interpolate the picture row between K[r-1] and K[r] ----
+            if (r <= n - 1 && (kFull || npix > 0)) {
+                Taps Ta;
+                Ta.build(wa);
+                const uint2 px = interpolate8(Ta, ta, Tb, tb, kmin);
+                const int y = t.offset + 2 * (r - 1);
+                store8(y + 1, px);
+                if (t.copy_kept) store8(y, make_uint2(wa[1], wa[2]));
+                if (r == n - 1) {                                               // K[r] is the last kept row
+                    if (t.offset == 0) store8(t.height - 1, make_uint2(wb[1], wb[2]));
+                    if (t.copy_kept) store8(y + 2, make_uint2(wb[1], wb[2]));
                 }
-                M[i][0] = P[i][0]; M[i][1] = P[i][1]; M[i][2] = P[i][2]; M[i][3] = P[i][3];
             }
-        }
-        if constexpr (kClustered) cl::sync_all(); else __syncthreads();
-
-        // ---- B[r] = wrap8(H7(L) >> 4) per buffer; keys for the min; M += B ----
-        uint32_t kmin[4] = { tkey, tkey, tkey, tkey };
-#pragma unroll
-        for (int i = 0; i < kNumCost; ++i) {
-            const uint16_t* row = Lrow + i * LS + lx;
-            const uint2 lh = *reinterpret_cast<const uint2*>(row - 4);      // (l-4,l-3) (l-2,l-1)
-            const uint4 own = *reinterpret_cast<const uint4*>(row);         // (l0,l1) .. (l6,l7)
-            const uint2 rh = *reinterpret_cast<const uint2*>(row + 8);      // (l8,l9) (l10,l11)
-            const uint32_t Wm2 = lh.x, Wm1 = lh.y, W0 = own.x, W1 = own.y, W2 = own.z, W3 = own.w, W4 = rh.x, W5 = rh.y;
-            // Z_k = W[k-1]+W[k]+W[k+1] (even / odd triples), X_k = Z_k + W[k-2];
-            // H7_k = Z_k + (X_k.hi, X_{k+1}.lo)  -> lanes (sum l[2k-3..2k+3], sum l[2k-2..2k+4])
-            const uint32_t Z0 = Wm1 + W0 + W1, Z1 = W0 + W1 + W2, Z2 = W1 + W2 + W3, Z3 = W2 + W3 + W4, Z4 = W3 + W4 + W5;
-            const uint32_t X0 = Z0 + Wm2, X1 = Z1 + Wm1, X2 = Z2 + W0, X3 = Z3 + W1, X4 = Z4 + W2;
-            uint32_t H[4];
-            H[0] = Z0 + __funnelshift_r(X0, X1, 16);
-            H[1] = Z1 + __funnelshift_r(X1, X2, 16);
-            H[2] = Z2 + __funnelshift_r(X2, X3, 16);
-            H[3] = Z3 + __funnelshift_r(X3, X4, 16);
-            uint32_t Bq[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                Bq[q] = (H[q] >> 4) & 0x00FF00FFu;
-                M[i][q] += Bq[q];
-                const uint32_t key = (H[q] & 0x0FF00FF0u) | rank2(i);
-                kmin[q] = __vminu2(kmin[q], key);
-            }
-            // hand the blurred row to the next pass of this frame
-            if (exporting) state_store8(t.out, i, r, x0, S, make_uint2(pack4(Bq[0], Bq[1]), pack4(Bq[2], Bq[3])));
-        }
-
-        // ---- interpolate the picture row between K[r-1] and K[r] ----
-        if (r <= n - 1 && npix > 0) {
-            Taps c, nx;
-            c.build(wa); nx.build(wb);
-            const uint2 px = interpolate8(c, nx, sg_prev, kmin);
-            store8(plane + (long long)(t.offset + 2 * (r - 1) + 1) * pitch, px);
-            if (t.copy_kept) store8(plane + (long long)(t.offset + 2 * (r - 1)) * pitch, make_uint2(wa[1], wa[2]));
-        }
 
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { wa[q] = wb[q]; wb[q] = wc[q]; wc[q] = wpre[q]; }
-    }
+            for (int q = 0; q < 4; ++q) { wa[q] = wb[q]; wb[q] = wc[q]; }
+            ta = tb; tb = tc;
+        }
+    };
+    // warp-uniform choice, so that a warp never splits over the two copies of the row barrier
+#ifdef SN_HOST_EMULATION
+    const bool warp_full = npix == kCols;
+#else
+    const bool warp_full = __all_sync(0xFFFFFFFFu, npix == kCols);
+#endif
+    if (warp_full) sweep(std::true_type{}); else sweep(std::false_type{});
 }
-
-inline size_t smem_bytes(int seg_cols) { return (size_t)2 * kNumCost * (seg_cols + 2 * kLPad) * sizeof(uint16_t); }
 
 }  // namespace u8k
 }  // namespace sn

@@ -43,7 +43,7 @@ int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long lo
         t.thr_f = thresholds[q];
         t.thr_i = sample_bytes == 1 ? ((int)thresholds[q] & 0xFF) : ((int)thresholds[q] & 0xFFFF);
         t.in = geo[q].in; t.out = geo[q].out;
-        sn::LaunchGeometry g{ S, Hb };
+        const sn::LaunchGeometry g = sn::make_geometry(S, Hb);
         const unsigned G = (unsigned)cluster;
         const int cols = sample_bytes == 1 ? sn::u8k::kCols : sn::wide::kCols;
         if (S % (int)(G * cols) != 0) return -1;

@@ -100,7 +100,8 @@ def test_emulated_kernel_matches_oracle(emul, fmtname, w, h, kw, kind):
         assert_planes_equal(got, exp[:3], f"{fmtname} {w}x{h} {kw} frame {i}")
 
 
-CLUSTER_CASES = [("Y8", 120, 20, dict(order=1), 2), ("YV12", 250, 36, dict(order=0, aa=48, aac=48), 4), ("Y8", 64, 12, dict(order=2, aa=20), 8),
+CLUSTER_CASES = [("Y8", 128, 20, dict(order=1), 2), ("YV12", 256, 36, dict(order=0, aa=48, aac=48), 4), ("YV12", 512, 24, dict(order=2, aa=48, aac=48), 8),
+                 ("Y8", 120, 20, dict(order=1), 2), ("YV12", 250, 36, dict(order=0, aa=48, aac=48), 4), ("Y8", 64, 12, dict(order=2, aa=20), 8),
                  ("Y16", 120, 20, dict(order=1), 2), ("YUV420P10", 250, 36, dict(order=0, aa=48, aac=48), 4), ("YUV420PS", 120, 24, dict(order=2, aa=48, aac=24), 2),
                  ("Y32", 64, 12, dict(order=1), 8), ("YUV422P16", 68, 30, dict(order=2, aa=30, aac=90), 2)]
 
