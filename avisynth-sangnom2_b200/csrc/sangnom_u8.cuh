@@ -33,9 +33,10 @@ namespace sn {
 namespace u8k {
 
 constexpr int kCols = 8;           // pool columns per thread
-constexpr int kLPad = 8;           // u16 elements of padding on each side of a shared L row (16 B)
-constexpr int kRing = 4;           // kept-row ring slots
-constexpr int kAhead = 3;          // rows staged ahead of the row being consumed
+constexpr int kLEntry = 2 * kNumCost + 1;   // uint2 words per thread entry of the shared L rows: 9 costs x 2 halves + 1 pad (152 B: conflict-free)
+constexpr int kT3Ring = 4;         // 3-tap byte ring slots (thread-private)
+constexpr int kRing = 8;           // kept-row ring slots: rows r-1 .. r+1 in use, up to r+kAhead in flight
+constexpr int kAhead = 4;          // rows staged ahead of the row being consumed
 constexpr int kRingPad = 16;       // bytes of halo on each side of a staged row segment
 
 // rank of cost buffer i in the reference's tie order (4,5,3,6,2,7,1,8,0)
@@ -203,18 +204,20 @@ __device__ __forceinline__ uint2 load8_guarded(const uint8_t* __restrict__ row, 
 }
 
 // Shared memory of one block (seg_cols pool columns, T = seg_cols / 8 threads):
-//   L     [2 parities][9 costs][2 halves][T + 2] uint2   vertical sums as 16-bit lanes: half 0 = columns 0..3 of
-//         every thread, half 1 = columns 4..7 (entry -1 / T: the neighbour segment's edge or the clamp). A thread
-//         reads half1[t-1], half0[t], half1[t], half0[t+1]: consecutive lanes touch consecutive 8-byte words.
+//   L     [2 parities][T + 2 entries][9 costs][2 halves] uint2 (+1 pad word per entry): the vertical sums of a
+//         thread's 8 columns as 16-bit lanes, half 0 = columns 0..3, half 1 = columns 4..7; entry 0 and T+1 hold the
+//         neighbour segment's edge or the clamp. Entries are 152 bytes apart, so consecutive lanes hit distinct
+//         banks with 8-byte accesses and every per-cost offset is an immediate.
 //   ring  [kRing][ring_stride]  staged kept rows, row position p at offset p - seg_x0 + kRingPad
+//   t3    [kT3Ring][T] uint4    3-tap bytes of the kept rows (thread-private slots)
 //   mbar  [kRing]               one mbarrier per ring slot
 //   task                        this block's PlaneTask
 inline __host__ __device__ int ring_stride(int seg_cols) { return (seg_cols + 2 * kRingPad + 15) & ~15; }
-inline __host__ __device__ int l_half_stride(int seg_cols) { return seg_cols / kCols + 2; }                  // uint2 entries
+inline __host__ __device__ size_t l_bytes(int seg_cols) { return (size_t)2 * (seg_cols / kCols + 2) * kLEntry * sizeof(uint2); }
 inline size_t smem_bytes(int seg_cols)
 {
-    return (size_t)2 * kNumCost * 2 * l_half_stride(seg_cols) * sizeof(uint2) + (size_t)kRing * ring_stride(seg_cols) + kRing * sizeof(stage::Mbar) +
-           ((sizeof(PlaneTask) + 15) & ~(size_t)15);
+    return ((l_bytes(seg_cols) + 15) & ~(size_t)15) + (size_t)kRing * ring_stride(seg_cols) + (size_t)kT3Ring * (seg_cols / kCols) * sizeof(uint4) +
+           kRing * sizeof(stage::Mbar) + ((sizeof(PlaneTask) + 15) & ~(size_t)15);
 }
 
 template <int kMaxThreads, int kMinBlocks, bool kClustered>
@@ -227,11 +230,12 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     const unsigned crank = kClustered ? cl::rank() : 0u;
     const int S = g.S;
     const uint32_t keymask = g.key_mask;                            // 0x0FF00FF0, kept in a register so (sum & mask) | rank is one LOP3
-    const int HS = l_half_stride(seg_cols);
+    const int tid = (int)threadIdx.x, T = seg_cols / kCols;
     uint2* const Lbase = reinterpret_cast<uint2*>(smem_raw);
     const int rstride = ring_stride(seg_cols);
-    uint8_t* const ring = smem_raw + (size_t)2 * kNumCost * 2 * HS * sizeof(uint2);
-    stage::Mbar* const mbar = reinterpret_cast<stage::Mbar*>(ring + (size_t)kRing * rstride);
+    uint8_t* const ring = smem_raw + ((l_bytes(seg_cols) + 15) & ~(size_t)15);
+    uint4* const t3ring = reinterpret_cast<uint4*>(ring + (size_t)kRing * rstride);
+    stage::Mbar* const mbar = reinterpret_cast<stage::Mbar*>(t3ring + (size_t)kT3Ring * T);
     // the task lives in shared memory: its rarely used fields (cost-state regions, pitches) are re-read where needed
     // instead of occupying registers for the whole sweep
     {
@@ -243,7 +247,6 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     const PlaneTask& t = *reinterpret_cast<const PlaneTask*>(mbar + kRing);
 
     const int W = t.width, n = t.kept_rows, R = t.sweep_rows;
-    const int tid = (int)threadIdx.x, T = seg_cols / kCols;
     const int lx = tid * kCols;                                     // column inside the segment
     const int seg_x0 = (int)crank * seg_cols;
     const int x0 = seg_x0 + lx;                                     // pool column
@@ -255,6 +258,7 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     // which of my 8 columns carry pixels: all, none, or a prefix (the one thread that straddles W)
     const int npix = min(max(W - x0, 0), kCols);
     const bool edge = npix > 0 && (x0 == 0 || x0 + 11 > W - 1);
+    const bool vec_out = ((reinterpret_cast<uintptr_t>(t.plane) | (uintptr_t)t.pitch) & 7) == 0 && npix == kCols;   // aligned 8-byte stores
 
     // ---- staging of kept rows: positions [lo, hi) of every kept row go to ring offset (position - seg_x0 + 16) ----
     const int lo = max(seg_x0 - kRingPad, 0), hi = min(seg_x0 + seg_cols + kRingPad, wpad);
@@ -281,9 +285,10 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
         if (kClustered && seg_first) *reinterpret_cast<uint2*>(s - 8) = v[1];
         if (kClustered && seg_last) *reinterpret_cast<uint2*>(s + 8) = v[2];
     };
+    // wait until kept row j has landed in the ring (first use of a row only)
+    auto await_row = [&](int j) { if (bulk) stage::mbar_wait(&mbar[j & (kRing - 1)], (unsigned)(j / kRing) & 1u); };
     // my window of kept row j (bytes x0-4 .. x0+11) out of the ring, picture edges replicated
-    auto take_window = [&](int j, uint32_t (&w)[4]) {
-        if (bulk) stage::mbar_wait(&mbar[j & (kRing - 1)], (unsigned)(j / kRing) & 1u);
+    auto window = [&](int j, uint32_t (&w)[4]) {
         const uint8_t* s = slot_of(j) + kRingPad + lx;
         w[0] = *reinterpret_cast<const uint32_t*>(s - 4);
         const uint2 own = *reinterpret_cast<const uint2*>(s);
@@ -291,11 +296,12 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
         w[3] = *reinterpret_cast<const uint32_t*>(s + 8);
         if (edge) fix_edges(w, x0, W);
     };
+    auto t3_put = [&](int j, const Tap3& v) { t3ring[(size_t)(j & (kT3Ring - 1)) * T + tid] = make_uint4(v.f[0], v.f[1], v.b[0], v.b[1]); };
+    auto t3_get = [&](int j, Tap3& v) { const uint4 q = t3ring[(size_t)(j & (kT3Ring - 1)) * T + tid]; v.f[0] = q.x; v.f[1] = q.y; v.b[0] = q.z; v.b[1] = q.w; };
     // my 8 bytes of a picture row of the dst plane
     auto store8 = [&](int y, uint2 v) {
         uint8_t* const row = static_cast<uint8_t*>(t.plane) + (long long)y * t.pitch;
-        const bool vec_out = ((reinterpret_cast<uintptr_t>(t.plane) | (uintptr_t)t.pitch) & 7) == 0;
-        if (npix == kCols && vec_out) { *reinterpret_cast<uint2*>(row + x0) = v; return; }
+        if (vec_out) { *reinterpret_cast<uint2*>(row + x0) = v; return; }
 #pragma unroll
         for (int b = 0; b < 8; ++b) if (b < npix) row[x0 + b] = (uint8_t)(((b < 4 ? v.x : v.y) >> (8 * (b & 3))) & 0xFFu);
     };
@@ -318,10 +324,8 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
         }
     }
 
-    // ---- running term M = B[r-1] + P[r] (+ leak); B[0] = 0 so M starts as P[1] ----
+    // ---- running term M = B[r-1] + P[r] (+ leak); B[0] = 0 so M starts as P[1]. The only loop-carried registers. ----
     uint32_t M[kNumCost][4];
-    uint32_t wa[4] = {}, wb[4] = {}, wc[4] = {};      // windows of K[r-1], K[r], K[r+1]
-    Tap3 ta{}, tb{}, tc{};                             // their 3-tap bytes
 
     // Stale costs of pool row `row` for my columns: what the previous pass of the frame left there.
     auto stale_costs = [&](int row, uint32_t (&Pb)[kNumCost][2]) {
@@ -332,162 +336,175 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
             Pb[i][0] = v.x; Pb[i][1] = v.y;
         }
     };
-    // Raw cost row `row` (pool row index = pair (K[row-1], K[row])) as bytes. kFull: this thread has 8 pixel columns.
-    auto cost_bytes = [&](auto full, int row, const Taps& c, const Tap3& c3, const Taps& nx, const Tap3& n3, uint32_t (&Pb)[kNumCost][2]) {
-        constexpr bool kFull = decltype(full)::value;
-        const bool pair = row <= n - 1;
-        if (kFull) {
-            if (pair) pair_costs(c, c3, nx, n3, Pb); else stale_costs(row, Pb);
-        } else {
-            stale_costs(row, Pb);
-            if (pair && npix > 0) {                      // the straddling thread: pixels left, stale right
-                const uint32_t pixmask_lo = npix >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (4 - npix)));
-                const uint32_t pixmask_hi = npix <= 4 ? 0u : (0xFFFFFFFFu >> (8 * (8 - npix)));
-                uint32_t Px[kNumCost][2];
-                pair_costs(c, c3, nx, n3, Px);
+    // Pixel costs of a pair merged into stale costs for the thread that straddles the picture's right edge.
+    auto straddle_costs = [&](const Taps& c, const Tap3& c3, const Taps& nx, const Tap3& n3, uint32_t (&Pb)[kNumCost][2]) {
+        const uint32_t pixmask_lo = npix >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (4 - npix)));
+        const uint32_t pixmask_hi = npix <= 4 ? 0u : (0xFFFFFFFFu >> (8 * (8 - npix)));
+        uint32_t Px[kNumCost][2];
+        pair_costs(c, c3, nx, n3, Px);
 #pragma unroll
-                for (int i = 0; i < kNumCost; ++i) {
-                    Pb[i][0] = (Px[i][0] & pixmask_lo) | (Pb[i][0] & ~pixmask_lo);
-                    Pb[i][1] = (Px[i][1] & pixmask_hi) | (Pb[i][1] & ~pixmask_hi);
-                }
-            }
+        for (int i = 0; i < kNumCost; ++i) {
+            Pb[i][0] = (Px[i][0] & pixmask_lo) | (Pb[i][0] & ~pixmask_lo);
+            Pb[i][1] = (Px[i][1] & pixmask_hi) | (Pb[i][1] & ~pixmask_hi);
         }
     };
 
     {
-        Taps Ta{}, Tb{};
+        uint32_t Pb[kNumCost][2];
+        if (npix < kCols || n < 2) stale_costs(1, Pb);
         if (npix > 0) {
-            take_window(0, wa);
+            uint32_t wa[4], wb[4];
+            Taps Ta, Tb;
+            Tap3 ta, tb;
+            await_row(0);
+            window(0, wa);
             Ta.build(wa);
             tap3_row(Ta, ta);
-            if (n >= 2) { take_window(1, wb); Tb.build(wb); tap3_row(Tb, tb); }
+            t3_put(0, ta);
             // border row without a neighbour pair (reference GetFrame :380-391) and, for a one-pair-less plane, the kept row
             if (t.offset != 0) store8(0, make_uint2(wa[1], wa[2]));
             if (n == 1) {
                 if (t.offset == 0) store8(t.height - 1, make_uint2(wa[1], wa[2]));
                 if (t.copy_kept) store8(t.offset, make_uint2(wa[1], wa[2]));
+            } else {
+                await_row(1);
+                window(1, wb);
+                Tb.build(wb);
+                tap3_row(Tb, tb);
+                t3_put(1, tb);
+                if (npix == kCols) pair_costs(Ta, ta, Tb, tb, Pb); else straddle_costs(Ta, ta, Tb, tb, Pb);
             }
         }
-        uint32_t Pb[kNumCost][2];
-        if (npix == kCols) cost_bytes(std::true_type{}, 1, Ta, ta, Tb, tb, Pb);
-        else cost_bytes(std::false_type{}, 1, Ta, ta, Tb, tb, Pb);
 #pragma unroll
         for (int i = 0; i < kNumCost; ++i) {
             M[i][0] = lanes_lo(Pb[i][0]) + leak(i); M[i][1] = lanes_hi(Pb[i][0]) + leak(i);
             M[i][2] = lanes_lo(Pb[i][1]) + leak(i); M[i][3] = lanes_hi(Pb[i][1]) + leak(i);
         }
     }
-    // every thread has left ring slot 0 before it is refilled; all blocks of a cluster run before the first DSMEM store
-    if constexpr (kClustered) cl::sync_all(); else __syncthreads();
+    // all blocks of a cluster run before the first DSMEM store
+    if constexpr (kClustered) cl::sync_all();
 
     const uint32_t tkey = (uint32_t)min(t.thr_i + 1, 4095) * 0x00100010u;    // (thr+1) << 4 in both lanes
     const bool exporting = t.out.a != nullptr || t.out.b != nullptr;
 
-    // The sweep. Instantiated twice: kFull for warps whose every thread owns 8 pixel columns (no stale-state or
-    // masking code on the hot path), general for warps that hold pad / stale columns. Both run the same barriers.
-    auto sweep = [&](auto full) {
-        constexpr bool kFull = decltype(full)::value;
-        for (int r = 1; r <= R; ++r) {
-            // wa = K[r-1], wb = K[r]; stage the ring, take K[r+1]
-            if (seg_has_pixels) {
-                if (bulk) {
-                    if (tid == 0 && r + kAhead < n) issue_row(r + kAhead);
-                } else {
-                    if (r + kAhead - 1 < n) coop_store(r + kAhead - 1, pre);
-                    if (r + kAhead < n) coop_load(r + kAhead, pre);
-                }
+    // One pool row. kFull: every thread of the warp owns 8 pixel columns (no stale-state or masking code on the hot
+    // path). kPair: row r+1 is a pair row (r + 1 <= n - 1), i.e. its costs come from pixels.
+    auto row_step = [&](auto full, auto pairrow, int r) {
+        constexpr bool kFull = decltype(full)::value, kPair = decltype(pairrow)::value;
+        const bool pixels = kFull || npix > 0;
+        // stage the ring
+        if (seg_has_pixels) {
+            if (bulk) {
+                if (tid == 0 && r + kAhead < n) issue_row(r + kAhead);
+            } else {
+                if (r + kAhead - 1 < n) coop_store(r + kAhead - 1, pre);
+                if (r + kAhead < n) coop_load(r + kAhead, pre);
             }
-            Taps Tb{}, Tc{};
-            if (kFull || npix > 0) {
+        }
+        uint32_t wb[4];                                  // K[r]: upper row of the pair whose costs are formed, lower row of the interpolation
+        Taps Tb;
+        Tap3 tb;
+
+        // ---- P[r+1], L = M + P[r+1] -> shared row; M keeps P[r+1] until B[r] is known ----
+        uint2* const Lrow = Lbase + ((size_t)(r & 1) * (T + 2) + 1 + tid) * kLEntry;      // my entry
+        {
+            uint32_t Pb[kNumCost][2];
+            if (!kFull || !kPair) stale_costs(r + 1, Pb);
+            if (kPair && pixels) {
+                uint32_t wc[4];
+                Taps Tc;
+                Tap3 tc;
+                window(r, wb);
                 Tb.build(wb);
-                if (r + 1 <= n - 1) { take_window(r + 1, wc); Tc.build(wc); tap3_row(Tc, tc); }
+                t3_get(r, tb);
+                await_row(r + 1);
+                window(r + 1, wc);
+                Tc.build(wc);
+                tap3_row(Tc, tc);
+                t3_put(r + 1, tc);
+                if (kFull) pair_costs(Tb, tb, Tc, tc, Pb); else straddle_costs(Tb, tb, Tc, tc, Pb);
             }
-
-            // ---- P[r+1], L = M + P[r+1] -> shared row; M keeps P[r+1] until B[r] is known ----
-            uint2* const Lrow = Lbase + (size_t)(r & 1) * kNumCost * 2 * HS + 1 + tid;     // half 0 of cost 0, my entry
-            {
-                uint32_t Pb[kNumCost][2];
-                cost_bytes(full, r + 1, Tb, tb, Tc, tc, Pb);
-#pragma unroll
-                for (int i = 0; i < kNumCost; ++i) {
-                    const uint32_t P0 = lanes_lo(Pb[i][0]), P1 = lanes_hi(Pb[i][0]), P2 = lanes_lo(Pb[i][1]), P3 = lanes_hi(Pb[i][1]);
-                    const uint2 Lxy = make_uint2(M[i][0] + P0 - leak(i), M[i][1] + P1 - leak(i));
-                    const uint2 Lzw = make_uint2(M[i][2] + P2 - leak(i), M[i][3] + P3 - leak(i));
-                    uint2* const h0 = Lrow + (size_t)i * 2 * HS;
-                    uint2* const h1 = h0 + HS;
-                    *h0 = Lxy;
-                    *h1 = Lzw;
-                    if (seg_first) {
-                        if (plane_first) { const uint32_t e = (Lxy.x & 0xFFFFu) * 0x00010001u; h1[-1] = make_uint2(e, e); }      // clamp at column 0
-                        else {                                                       // my first columns are the left neighbour's right halo
-                            cl::store_remote(&h0[T].x, crank - 1, Lxy.x);
-                            cl::store_remote(&h0[T].y, crank - 1, Lxy.y);
-                        }
-                    }
-                    if (seg_last) {
-                        if (plane_last) { const uint32_t e = (Lzw.y >> 16) * 0x00010001u; h0[1] = make_uint2(e, e); }           // clamp at column S-1
-                        else {                                                       // my last columns are the right neighbour's left halo
-                            cl::store_remote(&h1[-T].x, crank + 1, Lzw.x);
-                            cl::store_remote(&h1[-T].y, crank + 1, Lzw.y);
-                        }
-                    }
-                    M[i][0] = P0; M[i][1] = P1; M[i][2] = P2; M[i][3] = P3;
-                }
-            }
-            if constexpr (kClustered) cl::sync_all(); else __syncthreads();
-
-            // ---- per cost: 7-tap sum, key = (B << 4) | rank, M = P[r+1] + B (+ leak), min over the keys ----
-            uint32_t kmin[4] = { tkey, tkey, tkey, tkey };
-            uint32_t held[4] = {};
-            const StateRow out = exporting ? state_row(t.out, r, x0, S) : StateRow{ nullptr, 0 };
 #pragma unroll
             for (int i = 0; i < kNumCost; ++i) {
-                const uint2* const h0 = Lrow + (size_t)i * 2 * HS;
-                const uint2* const h1 = h0 + HS;
-                const uint2 lh = h1[-1];        // (l-4,l-3) (l-2,l-1)
-                const uint2 oa = h0[0];         // (l0,l1) (l2,l3)
-                const uint2 ob = h1[0];         // (l4,l5) (l6,l7)
-                const uint2 rh = h0[1];         // (l8,l9) (l10,l11)
-                const uint32_t Wm2 = lh.x, Wm1 = lh.y, W0 = oa.x, W1 = oa.y, W2 = ob.x, W3 = ob.y, W4 = rh.x, W5 = rh.y;
-                // Z_k = W[k-1]+W[k]+W[k+1] (even / odd triples), X_k = Z_k + W[k-2];
-                // H7_k = Z_k + (X_k.hi, X_{k+1}.lo)  -> lanes (sum l[2k-3..2k+3], sum l[2k-2..2k+4])
-                const uint32_t Z0 = Wm1 + W0 + W1, Z1 = W0 + W1 + W2, Z2 = W1 + W2 + W3, Z3 = W2 + W3 + W4, Z4 = W3 + W4 + W5;
-                const uint32_t X0 = Z0 + Wm2, X1 = Z1 + Wm1, X2 = Z2 + W0, X3 = Z3 + W1, X4 = Z4 + W2;
-                uint32_t key[4];
-                key[0] = ((Z0 + __funnelshift_r(X0, X1, 16)) & keymask) | rank2(i);
-                key[1] = ((Z1 + __funnelshift_r(X1, X2, 16)) & keymask) | rank2(i);
-                key[2] = ((Z2 + __funnelshift_r(X2, X3, 16)) & keymask) | rank2(i);
-                key[3] = ((Z3 + __funnelshift_r(X3, X4, 16)) & keymask) | rank2(i);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    M[i][q] += key[q] >> 4;                                     // LEA.HI: P[r+1] + B[r] + leak(i)
-                    if (i & 1) kmin[q] = __vimin3_u16x2(kmin[q], held[q], key[q]);
-                    else if (i == kNumCost - 1) kmin[q] = __vminu2(kmin[q], key[q]);
-                    else held[q] = key[q];
+                const uint32_t P0 = lanes_lo(Pb[i][0]), P1 = lanes_hi(Pb[i][0]), P2 = lanes_lo(Pb[i][1]), P3 = lanes_hi(Pb[i][1]);
+                const uint2 Lxy = make_uint2(M[i][0] + P0 - leak(i), M[i][1] + P1 - leak(i));
+                const uint2 Lzw = make_uint2(M[i][2] + P2 - leak(i), M[i][3] + P3 - leak(i));
+                Lrow[2 * i] = Lxy;
+                Lrow[2 * i + 1] = Lzw;
+                if (seg_first) {
+                    if (plane_first) { const uint32_t e = (Lxy.x & 0xFFFFu) * 0x00010001u; Lrow[2 * i + 1 - kLEntry] = make_uint2(e, e); }      // clamp at column 0
+                    else {                                                       // my first columns are the left neighbour's right halo
+                        cl::store_remote(&Lrow[2 * i + T * kLEntry].x, crank - 1, Lxy.x);
+                        cl::store_remote(&Lrow[2 * i + T * kLEntry].y, crank - 1, Lxy.y);
+                    }
                 }
-                // hand the blurred row to the next pass of this frame
-                if (out.p != nullptr)
-                    *reinterpret_cast<uint2*>(out.p + i * out.stride) = make_uint2(pack4(key[0] >> 4, key[1] >> 4), pack4(key[2] >> 4, key[3] >> 4));
-            }
-
-            // ---- interpolate the picture row between K[r-1] and K[r] ----
-            if (r <= n - 1 && (kFull || npix > 0)) {
-                Taps Ta;
-                Ta.build(wa);
-                const uint2 px = interpolate8(Ta, ta, Tb, tb, kmin);
-                const int y = t.offset + 2 * (r - 1);
-                store8(y + 1, px);
-                if (t.copy_kept) store8(y, make_uint2(wa[1], wa[2]));
-                if (r == n - 1) {                                               // K[r] is the last kept row
-                    if (t.offset == 0) store8(t.height - 1, make_uint2(wb[1], wb[2]));
-                    if (t.copy_kept) store8(y + 2, make_uint2(wb[1], wb[2]));
+                if (seg_last) {
+                    if (plane_last) { const uint32_t e = (Lzw.y >> 16) * 0x00010001u; Lrow[2 * i + kLEntry] = make_uint2(e, e); }             // clamp at column S-1
+                    else {                                                       // my last columns are the right neighbour's left halo
+                        cl::store_remote(&Lrow[2 * i + 1 - T * kLEntry].x, crank + 1, Lzw.x);
+                        cl::store_remote(&Lrow[2 * i + 1 - T * kLEntry].y, crank + 1, Lzw.y);
+                    }
                 }
+                M[i][0] = P0; M[i][1] = P1; M[i][2] = P2; M[i][3] = P3;
             }
-
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { wa[q] = wb[q]; wb[q] = wc[q]; }
-            ta = tb; tb = tc;
         }
+        if constexpr (kClustered) cl::sync_all(); else __syncthreads();
+
+        // ---- per cost: 7-tap sum, key = (B << 4) | rank, M = P[r+1] + B (+ leak), min over the keys ----
+        uint32_t kmin[4] = { tkey, tkey, tkey, tkey };
+        uint32_t held[4];
+        const StateRow out = exporting ? state_row(t.out, r, x0, S) : StateRow{ nullptr, 0 };
+#pragma unroll
+        for (int i = 0; i < kNumCost; ++i) {
+            const uint2 lh = Lrow[2 * i + 1 - kLEntry];     // (l-4,l-3) (l-2,l-1)
+            const uint2 oa = Lrow[2 * i];                   // (l0,l1) (l2,l3)
+            const uint2 ob = Lrow[2 * i + 1];               // (l4,l5) (l6,l7)
+            const uint2 rh = Lrow[2 * i + kLEntry];         // (l8,l9) (l10,l11)
+            const uint32_t Wm2 = lh.x, Wm1 = lh.y, W0 = oa.x, W1 = oa.y, W2 = ob.x, W3 = ob.y, W4 = rh.x, W5 = rh.y;
+            // Z_k = W[k-1]+W[k]+W[k+1] (even / odd triples), X_k = Z_k + W[k-2];
+            // H7_k = Z_k + (X_k.hi, X_{k+1}.lo)  -> lanes (sum l[2k-3..2k+3], sum l[2k-2..2k+4])
+            const uint32_t Z0 = Wm1 + W0 + W1, Z1 = W0 + W1 + W2, Z2 = W1 + W2 + W3, Z3 = W2 + W3 + W4, Z4 = W3 + W4 + W5;
+            const uint32_t X0 = Z0 + Wm2, X1 = Z1 + Wm1, X2 = Z2 + W0, X3 = Z3 + W1, X4 = Z4 + W2;
+            uint32_t key[4];
+            key[0] = ((Z0 + __funnelshift_r(X0, X1, 16)) & keymask) | rank2(i);
+            key[1] = ((Z1 + __funnelshift_r(X1, X2, 16)) & keymask) | rank2(i);
+            key[2] = ((Z2 + __funnelshift_r(X2, X3, 16)) & keymask) | rank2(i);
+            key[3] = ((Z3 + __funnelshift_r(X3, X4, 16)) & keymask) | rank2(i);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                M[i][q] += key[q] >> 4;                                     // LEA.HI: P[r+1] + B[r] + leak(i)
+                if (i & 1) kmin[q] = __vimin3_u16x2(kmin[q], held[q], key[q]);
+                else if (i == kNumCost - 1) kmin[q] = __vminu2(kmin[q], key[q]);
+                else held[q] = key[q];
+            }
+            // hand the blurred row to the next pass of this frame
+            if (out.p != nullptr)
+                *reinterpret_cast<uint2*>(out.p + i * out.stride) = make_uint2(pack4(key[0] >> 4, key[1] >> 4), pack4(key[2] >> 4, key[3] >> 4));
+        }
+
+        // ---- interpolate the picture row between K[r-1] and K[r] ----
+        if (pixels && (kPair || r == n - 1)) {
+            uint32_t wa[4];
+            Taps Ta;
+            Tap3 ta;
+            window(r - 1, wa);
+            Ta.build(wa);
+            t3_get(r - 1, ta);
+            if (!kPair) { window(r, wb); Tb.build(wb); t3_get(r, tb); }
+            const uint2 px = interpolate8(Ta, ta, Tb, tb, kmin);
+            const int y = t.offset + 2 * (r - 1);
+            store8(y + 1, px);
+            if (t.copy_kept) store8(y, make_uint2(wa[1], wa[2]));
+            if (!kPair) {                                                   // K[r] is the last kept row
+                if (t.offset == 0) store8(t.height - 1, make_uint2(wb[1], wb[2]));
+                if (t.copy_kept) store8(y + 2, make_uint2(wb[1], wb[2]));
+            }
+        }
+    };
+    auto sweep = [&](auto full) {
+        int r = 1;
+        for (; r <= n - 2; ++r) row_step(full, std::true_type{}, r);       // rows whose lower neighbour row is a pair row
+        for (; r <= R; ++r) row_step(full, std::false_type{}, r);          // the last picture row and rows swept for the next pass only
     };
     // warp-uniform choice, so that a warp never splits over the two copies of the row barrier
 #ifdef SN_HOST_EMULATION
