@@ -389,8 +389,9 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
 
     // One pool row. kFull: every thread of the warp owns 8 pixel columns (no stale-state or masking code on the hot
     // path). kPair: row r+1 is a pair row (r + 1 <= n - 1), i.e. its costs come from pixels.
-    auto row_step = [&](auto full, auto pairrow, int r) {
-        constexpr bool kFull = decltype(full)::value, kPair = decltype(pairrow)::value;
+    // kExport: some thread of the warp hands this row's blurred costs to the next pass of the frame.
+    auto row_step = [&](auto full, auto pairrow, auto exportrow, int r, const StateRow out) {
+        constexpr bool kFull = decltype(full)::value, kPair = decltype(pairrow)::value, kExport = decltype(exportrow)::value;
         const bool pixels = kFull || npix > 0;
         // stage the ring
         if (seg_has_pixels) {
@@ -431,21 +432,31 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
                 const uint2 Lzw = make_uint2(M[i][2] + P2 - leak(i), M[i][3] + P3 - leak(i));
                 Lrow[2 * i] = Lxy;
                 Lrow[2 * i + 1] = Lzw;
-                if (seg_first) {
-                    if (plane_first) { const uint32_t e = (Lxy.x & 0xFFFFu) * 0x00010001u; Lrow[2 * i + 1 - kLEntry] = make_uint2(e, e); }      // clamp at column 0
-                    else {                                                       // my first columns are the left neighbour's right halo
-                        cl::store_remote(&Lrow[2 * i + T * kLEntry].x, crank - 1, Lxy.x);
-                        cl::store_remote(&Lrow[2 * i + T * kLEntry].y, crank - 1, Lxy.y);
-                    }
-                }
-                if (seg_last) {
-                    if (plane_last) { const uint32_t e = (Lzw.y >> 16) * 0x00010001u; Lrow[2 * i + kLEntry] = make_uint2(e, e); }             // clamp at column S-1
-                    else {                                                       // my last columns are the right neighbour's left halo
-                        cl::store_remote(&Lrow[2 * i + 1 - T * kLEntry].x, crank + 1, Lzw.x);
-                        cl::store_remote(&Lrow[2 * i + 1 - T * kLEntry].y, crank + 1, Lzw.y);
-                    }
-                }
                 M[i][0] = P0; M[i][1] = P1; M[i][2] = P2; M[i][3] = P3;
+            }
+        }
+        // the two edge threads of the segment supply what lies beyond it: the clamp of the recursion at pool columns 0
+        // and S-1 (reference :144-152), or - plane split over a cluster - the neighbour block's halo (DSMEM)
+        if (seg_first) {
+#pragma unroll
+            for (int i = 0; i < kNumCost; ++i) {
+                const uint2 Lxy = Lrow[2 * i];
+                if (plane_first) { const uint32_t e = (Lxy.x & 0xFFFFu) * 0x00010001u; Lrow[2 * i + 1 - kLEntry] = make_uint2(e, e); }
+                else {
+                    cl::store_remote(&Lrow[2 * i + T * kLEntry].x, crank - 1, Lxy.x);
+                    cl::store_remote(&Lrow[2 * i + T * kLEntry].y, crank - 1, Lxy.y);
+                }
+            }
+        }
+        if (seg_last) {
+#pragma unroll
+            for (int i = 0; i < kNumCost; ++i) {
+                const uint2 Lzw = Lrow[2 * i + 1];
+                if (plane_last) { const uint32_t e = (Lzw.y >> 16) * 0x00010001u; Lrow[2 * i + kLEntry] = make_uint2(e, e); }
+                else {
+                    cl::store_remote(&Lrow[2 * i + 1 - T * kLEntry].x, crank + 1, Lzw.x);
+                    cl::store_remote(&Lrow[2 * i + 1 - T * kLEntry].y, crank + 1, Lzw.y);
+                }
             }
         }
         if constexpr (kClustered) cl::sync_all(); else __syncthreads();
@@ -453,7 +464,7 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
         // ---- per cost: 7-tap sum, key = (B << 4) | rank, M = P[r+1] + B (+ leak), min over the keys ----
         uint32_t kmin[4] = { tkey, tkey, tkey, tkey };
         uint32_t held[4];
-        const StateRow out = exporting ? state_row(t.out, r, x0, S) : StateRow{ nullptr, 0 };
+        uint8_t* outp = out.p;
 #pragma unroll
         for (int i = 0; i < kNumCost; ++i) {
             const uint2 lh = Lrow[2 * i + 1 - kLEntry];     // (l-4,l-3) (l-2,l-1)
@@ -478,8 +489,10 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
                 else held[q] = key[q];
             }
             // hand the blurred row to the next pass of this frame
-            if (out.p != nullptr)
-                *reinterpret_cast<uint2*>(out.p + i * out.stride) = make_uint2(pack4(key[0] >> 4, key[1] >> 4), pack4(key[2] >> 4, key[3] >> 4));
+            if (kExport) {
+                if (out.p != nullptr) *reinterpret_cast<uint2*>(outp) = make_uint2(pack4(key[0] >> 4, key[1] >> 4), pack4(key[2] >> 4, key[3] >> 4));
+                outp += out.stride;
+            }
         }
 
         // ---- interpolate the picture row between K[r-1] and K[r] ----
@@ -501,10 +514,28 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
             }
         }
     };
+    // does any thread of my warp export pool row r? (warp-uniform, so the two variants of a row keep warps whole)
+    auto export_row = [&](int r, StateRow& out) -> bool {
+        out = StateRow{ nullptr, 0 };
+        if (!exporting) return false;
+        out = state_row(t.out, r, x0, S);
+#ifdef SN_HOST_EMULATION
+        return out.p != nullptr;
+#else
+        return __any_sync(0xFFFFFFFFu, out.p != nullptr);
+#endif
+    };
     auto sweep = [&](auto full) {
         int r = 1;
-        for (; r <= n - 2; ++r) row_step(full, std::true_type{}, r);       // rows whose lower neighbour row is a pair row
-        for (; r <= R; ++r) row_step(full, std::false_type{}, r);          // the last picture row and rows swept for the next pass only
+        StateRow out;
+        for (; r <= n - 2; ++r) {                                           // rows whose lower neighbour row is a pair row
+            if (export_row(r, out)) row_step(full, std::true_type{}, std::true_type{}, r, out);
+            else row_step(full, std::true_type{}, std::false_type{}, r, out);
+        }
+        for (; r <= R; ++r) {                                               // the last picture row and rows swept for the next pass only
+            if (export_row(r, out)) row_step(full, std::false_type{}, std::true_type{}, r, out);
+            else row_step(full, std::false_type{}, std::false_type{}, r, out);
+        }
     };
     // warp-uniform choice, so that a warp never splits over the two copies of the row barrier
 #ifdef SN_HOST_EMULATION
