@@ -93,7 +93,7 @@ struct Slot {
     std::vector<FramePlan*> frames;      // frames of the chunk in flight (for the pageable copy-out)
 };
 
-constexpr int kSlots = 3;
+constexpr int kSlots = 4;
 constexpr int kTaskRing = 8;
 
 }  // namespace
@@ -256,6 +256,31 @@ int launch_passes(sn_ctx* ctx, const std::vector<std::vector<sn::PlaneTask>>& by
     return SN_OK;
 }
 
+// A run of bytes that is contiguous both in (pinned) host memory and in the device slot: one DMA transfer.
+struct Segment { char* host; char* dev; size_t bytes; };
+
+void add_segment(std::vector<Segment>& v, void* host, void* dev, size_t bytes)
+{
+    char* h = static_cast<char*>(host);
+    char* d = static_cast<char*>(dev);
+    if (!v.empty() && v.back().host + v.back().bytes == h && v.back().dev + v.back().bytes == d) v.back().bytes += bytes;
+    else v.push_back(Segment{ h, d, bytes });
+}
+
+cudaError_t flush_segments(std::vector<Segment>& v, cudaMemcpyKind kind, cudaStream_t stream)
+{
+    cudaError_t e = cudaSuccess;
+    for (const Segment& g : v) {
+        e = kind == cudaMemcpyHostToDevice ? cudaMemcpyAsync(g.dev, g.host, g.bytes, kind, stream) : cudaMemcpyAsync(g.host, g.dev, g.bytes, kind, stream);
+        if (e != cudaSuccess) break;
+    }
+    v.clear();
+    return e;
+}
+
+// SANGNOM_UPLOAD=field: upload only the kept rows of pinned contiguous planes (2-D DMA) instead of the whole plane.
+const bool g_upload_kept_only = [] { const char* v = getenv("SANGNOM_UPLOAD"); return v && std::strcmp(v, "field") == 0; }();
+
 // Copy the finished planes of a chunk from pinned staging to pageable destinations.
 int drain_slot(sn_ctx* ctx, Slot& s)
 {
@@ -369,11 +394,13 @@ int sangnom_cuda_create(const sn_config* cfg, sn_ctx** out)
     if (cfg->max_frames_in_flight > 0) {
         ctx->frames_in_flight = cfg->max_frames_in_flight;
     } else {
-        // default: three chunks of one frame per SM (so every launch can fill the GPU), capped at ~6 GB of
-        // device memory for planes + cost state (about 2.5 x the three planes of a frame)
+        // default: one frame per SM over the kSlots chunks in flight - chunks small enough that the pipeline's
+        // ramp (first upload, last download, one kernel latency) stays short, large enough that the chunks whose
+        // kernels overlap fill the GPU - capped at ~24 GB of device memory for planes + cost state (about 2.5 x
+        // the three planes of a frame)
         const double per_frame = 2.5 * 3.0 * (double)S * (double)cfg->pool_height * (double)cfg->sample_type;
-        const long long fit = (long long)(6.0e9 / per_frame);
-        ctx->frames_in_flight = (int)std::min<long long>(3LL * prop.multiProcessorCount, std::max<long long>(fit, 12));
+        const long long fit = (long long)(24.0e9 / per_frame);
+        ctx->frames_in_flight = (int)std::min<long long>(prop.multiProcessorCount, std::max<long long>(fit, 12));
     }
     auto bail = [&](cudaError_t err, const char* what) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
@@ -572,8 +599,11 @@ int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs
         const size_t first = next, last = std::min(frames.size(), next + chunk_frames);
         next = last;
 
-        // placement inside the slot
-        size_t plane_bytes = 0, state_bytes = 0, in_bytes = 0, out_bytes = 0, ntasks = 0;
+        // placement inside the slot: one region for the uploaded source rows and one for the finished planes,
+        // each filled in job order. LINEAR planes are packed at 16-byte granules (bulk copies and vector accesses
+        // need no more), so planes that are contiguous in host memory are contiguous on the device as well and their
+        // DMA transfers merge into one (a 518 KB chroma plane copied alone runs at ~39 GB/s, a merged run at ~53).
+        size_t src_bytes_total = 0, dst_bytes_total = 0, state_bytes = 0, in_bytes = 0, out_bytes = 0, ntasks = 0;
         for (size_t k = first; k < last; ++k) {
             FramePlan& f = frames[k];
             f.state_off = state_bytes;
@@ -585,21 +615,25 @@ int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs
                 const bool field = jb.mode == SN_MODE_FIELD;
                 if (!p.src_pinned) {                                   // kept rows packed by the CPU
                     p.up = Pass::STAGED; p.src_pitch = rowpad; p.src_bytes = rowpad * p.n; p.src_first = 0; p.src_step = rowpad;
-                    p.stage_in_off = in_bytes; in_bytes += align_up(p.src_bytes, 256);
-                } else if ((size_t)jb.src_pitch == row && row % 16 == 0) {   // whole source plane, one contiguous DMA
+                    p.stage_in_off = in_bytes; in_bytes += p.src_bytes;
+                } else if ((size_t)jb.src_pitch == row && row % 16 == 0 && !g_upload_kept_only) {   // whole source plane, contiguous DMA
                     p.up = Pass::LINEAR; p.src_pitch = row; p.src_bytes = row * src_rows;
                     p.src_first = field ? (size_t)jb.offset * row : 0; p.src_step = field ? 2 * row : row;
                 } else {                                               // kept rows by 2-D DMA
                     p.up = Pass::PITCHED; p.src_pitch = rowpad; p.src_bytes = rowpad * p.n; p.src_first = 0; p.src_step = rowpad;
                 }
-                p.src_off = plane_bytes; plane_bytes += align_up(p.src_bytes, 256);
-                if (!p.dst_pinned) { p.down = Pass::STAGED; p.dst_pitch = rowpad; p.stage_out_off = out_bytes; out_bytes += align_up(rowpad * p.H, 256); }
+                p.src_off = src_bytes_total; src_bytes_total += p.src_bytes;          // multiples of 16 in every class
+                if (!p.dst_pinned) { p.down = Pass::STAGED; p.dst_pitch = rowpad; p.stage_out_off = out_bytes; out_bytes += rowpad * p.H; }
                 else if ((size_t)jb.dst_pitch == row && row % 16 == 0) { p.down = Pass::LINEAR; p.dst_pitch = row; }
                 else { p.down = Pass::PITCHED; p.dst_pitch = rowpad; }
-                p.dst_off = plane_bytes; plane_bytes += align_up(p.dst_pitch * p.H, 256);
+                p.dst_off = dst_bytes_total; dst_bytes_total += p.dst_pitch * p.H;
                 ++ntasks;
             }
         }
+        const size_t dst_base = align_up(src_bytes_total, 256);
+        const size_t plane_bytes = dst_base + dst_bytes_total;
+        for (size_t k = first; k < last; ++k)
+            for (Pass& p : frames[k].passes) p.dst_off += dst_base;
         cudaError_t e;
         if ((e = s.planes.ensure(plane_bytes)) != cudaSuccess || (e = s.state.ensure(state_bytes)) != cudaSuccess ||
             (e = s.tasks.ensure(ntasks * sizeof(sn::PlaneTask))) != cudaSuccess ||
@@ -612,6 +646,7 @@ int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs
         cudaEventRecord(s.h2d_start, ctx->h2d);
         // ---- upload (the reference's kept-field BitBlt, SangNom2.cpp:361-377, becomes DMA + the kernel's own reads) ----
         std::vector<std::vector<sn::PlaneTask>> by_pass(3);
+        std::vector<Segment> up_segs, down_segs;
         for (size_t k = first; k < last && status == SN_OK; ++k) {
             FramePlan& f = frames[k];
             for (const sn_plane_job* c : f.copies) host_copy_plane(*c, sb);
@@ -623,20 +658,24 @@ int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs
                 const char* kept = static_cast<const char*>(jb.src) + (jb.mode == SN_MODE_FIELD ? (ptrdiff_t)jb.offset * jb.src_pitch : 0);
                 const size_t kept_step = (size_t)jb.src_pitch * (jb.mode == SN_MODE_FIELD ? 2 : 1);
                 char* dsrc = static_cast<char*>(s.planes.p) + p.src_off;
+                e = cudaSuccess;
                 if (p.up == Pass::STAGED) {
                     char* st = static_cast<char*>(s.stage_in.p) + p.stage_in_off;
                     for (int y = 0; y < p.n; ++y) std::memcpy(st + (size_t)y * p.src_pitch, kept + (size_t)y * kept_step, row);
-                    e = cudaMemcpyAsync(dsrc, st, p.src_bytes, cudaMemcpyHostToDevice, ctx->h2d);
+                    add_segment(up_segs, st, dsrc, p.src_bytes);
                 } else if (p.up == Pass::LINEAR) {
-                    e = cudaMemcpyAsync(dsrc, jb.src, p.src_bytes, cudaMemcpyHostToDevice, ctx->h2d);
+                    add_segment(up_segs, const_cast<void*>(jb.src), dsrc, p.src_bytes);
                 } else {
-                    e = cudaMemcpy2DAsync(dsrc, p.src_pitch, kept, kept_step, row, (size_t)p.n, cudaMemcpyHostToDevice, ctx->h2d);
+                    e = flush_segments(up_segs, cudaMemcpyHostToDevice, ctx->h2d);          // keep submission order
+                    if (e == cudaSuccess)
+                        e = cudaMemcpy2DAsync(dsrc, p.src_pitch, kept, kept_step, row, (size_t)p.n, cudaMemcpyHostToDevice, ctx->h2d);
                 }
                 if (e != cudaSuccess) { status = ctx->cuda_fail(e, "H2D copy"); break; }
                 ctx->stats.h2d_bytes += p.up == Pass::PITCHED ? row * p.n : p.src_bytes;
                 by_pass[q].push_back(make_task(ctx, p, static_cast<char*>(s.planes.p) + p.dst_off, p.dst_pitch, dsrc + p.src_first, p.src_step));
             }
         }
+        if (status == SN_OK && (e = flush_segments(up_segs, cudaMemcpyHostToDevice, ctx->h2d)) != cudaSuccess) status = ctx->cuda_fail(e, "H2D copy");
         if (status != SN_OK) break;
         // The task array rides the upload stream too: a small copy on the compute stream would queue on the
         // same DMA engine behind the NEXT chunks' bulk uploads and hold this chunk's kernels back.
@@ -661,17 +700,23 @@ int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs
                 const sn_plane_job& jb = *p.job;
                 const size_t row = (size_t)p.W * sb;
                 const char* dplane = static_cast<char*>(s.planes.p) + p.dst_off;
+                char* dplane_w = const_cast<char*>(dplane);
+                e = cudaSuccess;
                 if (p.down == Pass::STAGED)
-                    e = cudaMemcpyAsync(static_cast<char*>(s.stage_out.p) + p.stage_out_off, dplane, p.dst_pitch * p.H, cudaMemcpyDeviceToHost, ctx->d2h);
+                    add_segment(down_segs, static_cast<char*>(s.stage_out.p) + p.stage_out_off, dplane_w, p.dst_pitch * p.H);
                 else if (p.down == Pass::LINEAR)
-                    e = cudaMemcpyAsync(jb.dst, dplane, row * p.H, cudaMemcpyDeviceToHost, ctx->d2h);
-                else
-                    e = cudaMemcpy2DAsync(jb.dst, (size_t)jb.dst_pitch, dplane, p.dst_pitch, row, (size_t)p.H, cudaMemcpyDeviceToHost, ctx->d2h);
+                    add_segment(down_segs, jb.dst, dplane_w, row * p.H);
+                else {
+                    e = flush_segments(down_segs, cudaMemcpyDeviceToHost, ctx->d2h);
+                    if (e == cudaSuccess)
+                        e = cudaMemcpy2DAsync(jb.dst, (size_t)jb.dst_pitch, dplane, p.dst_pitch, row, (size_t)p.H, cudaMemcpyDeviceToHost, ctx->d2h);
+                }
                 if (e != cudaSuccess) { status = ctx->cuda_fail(e, "D2H copy"); break; }
                 ctx->stats.d2h_bytes += p.down == Pass::PITCHED ? row * p.H : p.dst_pitch * p.H;
             }
             s.frames.push_back(&f);
         }
+        if (status == SN_OK && (e = flush_segments(down_segs, cudaMemcpyDeviceToHost, ctx->d2h)) != cudaSuccess) status = ctx->cuda_fail(e, "D2H copy");
         if (status != SN_OK) break;
         if ((e = cudaEventRecord(s.d2h_done, ctx->d2h)) != cudaSuccess) { status = ctx->cuda_fail(e, "event"); break; }
         s.busy = true;

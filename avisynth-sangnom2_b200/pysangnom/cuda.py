@@ -133,6 +133,24 @@ def pinned_empty(shape, dtype):
 _owners = {}
 
 
+class PinnedArena:
+    """One cudaHostAlloc allocation handed out as consecutive numpy planes - how a batching host layer
+    stages frames: planes that are neighbours in host memory travel in one DMA transfer."""
+
+    def __init__(self, nbytes):
+        self.buf = pinned_empty((max(int(nbytes), 1),), np.uint8)
+        self.pos = 0
+
+    def take(self, shape, dtype, align=16):
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        start = (self.pos + align - 1) // align * align
+        if start + nbytes > self.buf.size:
+            raise MemoryError("pinned arena exhausted")
+        self.pos = start + nbytes
+        return self.buf[start:start + nbytes].view(dtype).reshape(shape)
+
+
 def make_job(src_ptr, src_pitch, dst_ptr, dst_pitch, width, dst_height, offset, mode, thr, plane, frame):
     return SnPlaneJob(src_ptr, src_pitch, dst_ptr, dst_pitch, width, dst_height, offset, mode, thr, plane, frame)
 

@@ -118,7 +118,7 @@ SN_API void sangnom_cuda_destroy(sn_ctx* ctx);
 /* HOST buffers. Pinned (cudaHostAlloc / cudaHostRegister) buffers are DMA'd directly; pageable
  * buffers go through the context's pinned staging. Jobs may be in any order; they are grouped by
  * `frame` and run in plane order. Synchronous: returns when every dst is complete. Frames are
- * pipelined internally (H2D | kernels | D2H on three streams). */
+ * pipelined internally (H2D | kernels | D2H on separate streams, four chunks of frames in flight). */
 SN_API int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs);
 
 /* DEVICE buffers: src/dst are device pointers on ctx's device. Asynchronous on `cuda_stream`, a
