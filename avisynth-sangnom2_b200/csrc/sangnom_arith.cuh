@@ -67,14 +67,18 @@ __device__ __forceinline__ I interpolate_rank(const I (&wc)[N], const I (&wn)[N]
 {
     const int q = p + kHalo;
     I a = wc[q], b = wn[q];
-    if (rank == 1) { a = tap3<T, I>(wc[q + 1], wc[q], wc[q - 1]); b = tap3<T, I>(wn[q - 1], wn[q], wn[q + 1]); }
-    if (rank == 2) { a = tap3<T, I>(wc[q - 1], wc[q], wc[q + 1]); b = tap3<T, I>(wn[q + 1], wn[q], wn[q - 1]); }
+    // ranks 1 and 2 average two 3-tap values; they differ only in which side neighbour is the first tap
+    const bool sg = rank == 1 || rank == 2, rev = rank == 1;
+    const I a1 = rev ? wc[q + 1] : wc[q - 1], a3 = rev ? wc[q - 1] : wc[q + 1];
+    const I sa = tap3<T, I>(a1, wc[q], a3);
+    const I sb = tap3<T, I>(rev ? wn[q - 1] : wn[q + 1], wn[q], rev ? wn[q + 1] : wn[q - 1]);
     if (rank == 3) { a = wc[q + 1]; b = wn[q - 1]; }
     if (rank == 4) { a = wc[q - 1]; b = wn[q + 1]; }
     if (rank == 5) { a = wc[q + 2]; b = wn[q - 2]; }
     if (rank == 6) { a = wc[q - 2]; b = wn[q + 2]; }
     if (rank == 7) { a = wc[q + 3]; b = wn[q - 3]; }
     if (rank == 8) { a = wc[q - 3]; b = wn[q + 3]; }
+    if (sg) { a = sa; b = sb; }
     return mean2(a, b);
 }
 

@@ -142,8 +142,9 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
         return nullptr;
     };
 
-    // Raw cost row `row` of the pool into P: pixels where I have them and the pair exists, else the handed-over state.
-    auto cost_row = [&](int row, I (&P)[kNumCost][kCols]) {
+    // Raw cost row `row` of the pool into P: pixels where I have them and the pair exists (windows wc = K[row-1],
+    // wn = K[row]), else the handed-over state.
+    auto cost_row = [&](int row, const I (&wc)[kWin], const I (&wn)[kWin], I (&P)[kNumCost][kCols]) {
         const bool pair = row <= n - 1;          // pool row j+1 holds the costs of the pair (K[j], K[j+1])
         const bool pixels = pair && npix > 0;
         if (!(pixels && npix == kCols)) {
@@ -156,9 +157,6 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
             }
         }
         if (pixels) {
-            I wc[kWin], wn[kWin];
-            load_window<T, I>(kept_row(row - 1), x0, W, vec, wc);
-            load_window<T, I>(kept_row(row), x0, W, vec, wn);
 #pragma unroll
             for (int c = 0; c < kCols; ++c) {
                 I cost[kNumCost];
@@ -171,8 +169,20 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
         }
     };
 
-    I M[kNumCost][kCols];                        // B[r-1] + P[r]; B[0] = 0
-    cost_row(1, M);
+    // Rolling register windows of three kept rows: wa = K[r-1], wb = K[r], wc = K[r+1]; each kept row is read from
+    // global memory once. M = B[r-1] + P[r] (B[0] = 0) is the only cost state carried down the rows.
+    I wa[kWin], wb[kWin], wc[kWin];
+    I M[kNumCost][kCols];
+#pragma unroll
+    for (int e = 0; e < kWin; ++e) { wa[e] = I(0); wb[e] = I(0); wc[e] = I(0); }
+    if (npix > 0) {
+        load_window<T, I>(kept_row(0), x0, W, vec, wb);
+        if (n > 1) load_window<T, I>(kept_row(1), x0, W, vec, wc);
+    }
+    cost_row(1, wb, wc, M);
+    // after this the loop invariant holds at r = 1: wa = K[0], wb = K[1]
+#pragma unroll
+    for (int e = 0; e < kWin; ++e) { wa[e] = wb[e]; wb[e] = wc[e]; }
 
     const int tkey = (int)min((long long)t.thr_i + 1, 0x7FFFFFFLL) << 4;      // (thr+1) << 4: "every cost above the threshold"
     const bool exporting = t.out.a != nullptr || t.out.b != nullptr;
@@ -181,27 +191,30 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
         // pull the kept row two iterations ahead towards L1 (no register cost)
         if (r + 3 <= n - 1 && npix > 0) prefetch_l1(kept_row(r + 3) + x0);
 
-        // ---- P[r+1]; L = M + P[r+1] into the shared row (and the neighbours' pads) ----
-        I P[kNumCost][kCols];
-        cost_row(r + 1, P);
+        // ---- P[r+1]; L = M + P[r+1] into the shared row (and the neighbours' pads); M keeps P[r+1] ----
+        if (r + 1 <= n - 1 && npix > 0) load_window<T, I>(kept_row(r + 1), x0, W, vec, wc);
         I* const Lrow = Lbase + (size_t)(r & 1) * kNumCost * LS + kHalo;
+        {
+            I P[kNumCost][kCols];
+            cost_row(r + 1, wb, wc, P);
 #pragma unroll
-        for (int i = 0; i < kNumCost; ++i) {
-            I* row = Lrow + i * LS;
-            I L[4];
+            for (int i = 0; i < kNumCost; ++i) {
+                I* row = Lrow + i * LS;
+                I L[4];
 #pragma unroll
-            for (int c = 0; c < kCols; ++c) L[c] = add2(M[i][c], P[i][c]);
-            if constexpr (Flavour<T>::kFloat) *reinterpret_cast<float4*>(row + lx) = make_float4(L[0], L[1], L[2], L[3]);
-            else *reinterpret_cast<uint4*>(row + lx) = make_uint4((uint32_t)L[0], (uint32_t)L[1], (uint32_t)L[2], (uint32_t)L[3]);
-            if (seg_first) {
-                if (plane_first) { row[-1] = L[0]; row[-2] = L[0]; row[-3] = L[0]; }                         // clamp at column 0
-                else { cl::store_remote(row + seg_cols, crank - 1, L[0]); cl::store_remote(row + seg_cols + 1, crank - 1, L[1]);
-                       cl::store_remote(row + seg_cols + 2, crank - 1, L[2]); }
-            }
-            if (seg_last) {
-                if (plane_last) { row[seg_cols] = L[3]; row[seg_cols + 1] = L[3]; row[seg_cols + 2] = L[3]; } // clamp at column S-1
-                else { cl::store_remote(row - 3, crank + 1, L[1]); cl::store_remote(row - 2, crank + 1, L[2]);
-                       cl::store_remote(row - 1, crank + 1, L[3]); }
+                for (int c = 0; c < kCols; ++c) { L[c] = add2(M[i][c], P[i][c]); M[i][c] = P[i][c]; }
+                if constexpr (Flavour<T>::kFloat) *reinterpret_cast<float4*>(row + lx) = make_float4(L[0], L[1], L[2], L[3]);
+                else *reinterpret_cast<uint4*>(row + lx) = make_uint4((uint32_t)L[0], (uint32_t)L[1], (uint32_t)L[2], (uint32_t)L[3]);
+                if (seg_first) {
+                    if (plane_first) { row[-1] = L[0]; row[-2] = L[0]; row[-3] = L[0]; }                         // clamp at column 0
+                    else { cl::store_remote(row + seg_cols, crank - 1, L[0]); cl::store_remote(row + seg_cols + 1, crank - 1, L[1]);
+                           cl::store_remote(row + seg_cols + 2, crank - 1, L[2]); }
+                }
+                if (seg_last) {
+                    if (plane_last) { row[seg_cols] = L[3]; row[seg_cols + 1] = L[3]; row[seg_cols + 2] = L[3]; } // clamp at column S-1
+                    else { cl::store_remote(row - 3, crank + 1, L[1]); cl::store_remote(row - 2, crank + 1, L[2]);
+                           cl::store_remote(row - 1, crank + 1, L[3]); }
+                }
             }
         }
         if constexpr (kClustered) cl::sync_all(); else __syncthreads();
@@ -246,34 +259,34 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
 #pragma unroll
                 for (int c = 0; c < kCols; ++c) {
                     if (c > 0) s += Lw[c + 7] - Lw[c];
-                    B4[c] = (s >> 4) & Flavour<T>::kMask;
-                    kmin[c] = min(kmin[c], (int)(((unsigned)s & ((unsigned)Flavour<T>::kMask << 4)) | (unsigned)k));
+                    const int key = (int)(((unsigned)s & ((unsigned)Flavour<T>::kMask << 4)) | (unsigned)k);   // wrapT(s / 16) << 4 | rank
+                    B4[c] = key >> 4;
+                    kmin[c] = min(kmin[c], key);
                 }
             }
 #pragma unroll
-            for (int c = 0; c < kCols; ++c) M[i][c] = add2(B4[c], P[i][c]);
+            for (int c = 0; c < kCols; ++c) M[i][c] = add2(B4[c], M[i][c]);
             if (out_ptr != nullptr) store4(out_ptr + i * out_stride, B4);
         }
 
         // ---- interpolate the picture row between K[r-1] and K[r] ----
         if (r <= n - 1 && npix > 0) {
-            I wc[kWin], wn[kWin];
-            load_window<T, I>(kept_row(r - 1), x0, W, vec, wc);
-            load_window<T, I>(kept_row(r), x0, W, vec, wn);
             I px[kCols];
 #pragma unroll
             for (int c = 0; c < kCols; ++c) {
                 int rank;
                 if constexpr (Flavour<T>::kFloat) rank = fmin[c] > t.thr_f ? 0 : frank[c];
                 else rank = kmin[c] & 15;
-                px[c] = interpolate_rank<T, I, kWin, kHalo>(wc, wn, c, rank);
+                px[c] = interpolate_rank<T, I, kWin, kHalo>(wa, wb, c, rank);
             }
             store_px(plane + (long long)(t.offset + 2 * (r - 1) + 1) * pitch, px);
             if (t.copy_kept) {
-                const I keptrow[4] = { wc[4], wc[5], wc[6], wc[7] };
+                const I keptrow[4] = { wa[4], wa[5], wa[6], wa[7] };
                 store_px(plane + (long long)(t.offset + 2 * (r - 1)) * pitch, keptrow);
             }
         }
+#pragma unroll
+        for (int e = 0; e < kWin; ++e) { wa[e] = wb[e]; wb[e] = wc[e]; }
     }
 }
 
