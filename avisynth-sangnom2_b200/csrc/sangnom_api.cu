@@ -9,11 +9,15 @@
 #include "sangnom_kernels.h"
 #include "sangnom_plan.h"
 
+#include <cuda.h>      // driver API types only; the entry point is looked up at run time (no libcuda link dependency)
+
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -72,7 +76,7 @@ struct Pass {
     size_t src_first = 0, src_step = 0;                 // kept row 0 and kept-row step inside it (bytes)
     size_t dst_off = 0, dst_pitch = 0;                  // device dst plane
     size_t stage_in_off = 0, stage_out_off = 0;
-    bool src_pinned = false, dst_pinned = false;
+    int src_pinned = 0, dst_pinned = 0;                // 0 = pageable, else 1 + pinned allocation index (PinnedLookup)
 };
 
 struct FramePlan {
@@ -91,6 +95,14 @@ struct Slot {
     cudaEvent_t h2d_start = nullptr, h2d_done = nullptr, k_start = nullptr, kernels_done = nullptr, d2h_start = nullptr, d2h_done = nullptr;
     bool busy = false;
     std::vector<FramePlan*> frames;      // frames of the chunk in flight (for the pageable copy-out)
+    uint64_t ticket = 0;                 // batch the chunk belongs to
+};
+
+// One submitted job list: the jobs are copied so that the plans may outlive the caller's array.
+struct Batch {
+    uint64_t ticket = 0;
+    std::vector<sn_plane_job> jobs;
+    std::vector<FramePlan> frames;
 };
 
 constexpr int kSlots = 4;
@@ -106,6 +118,9 @@ struct sn_ctx {
     cudaStream_t h2d = nullptr, d2h = nullptr, own_compute = nullptr;
     cudaEvent_t trace_base = nullptr;
     Slot slots[kSlots];
+    int next_slot = 0;                   // slots are used round-robin, so this is also the oldest one in flight
+    uint64_t last_ticket = 0;
+    std::deque<std::unique_ptr<Batch>> batches;
     // device-entry resources
     DevBuf dev_state;
     DevBuf dev_tasks[kTaskRing];
@@ -142,12 +157,53 @@ namespace {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-bool is_pinned_host(const void* p)
-{
-    cudaPointerAttributes a{};
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost;
-}
+// Which pinned allocation a host pointer lies in. DMA transfers may only be merged inside one allocation (a copy that
+// spans two cudaHostAlloc blocks fails even when they are neighbours in the address space), so pinned-ness and the
+// allocation's extent are looked up together; lookups are cached per submitted batch, one driver query per allocation.
+struct HostRange { uintptr_t lo = 0, hi = 0; };
+
+class PinnedLookup {
+    using GetAttr = CUresult (*)(void*, CUpointer_attribute, CUdeviceptr);
+    GetAttr get_ = nullptr;
+    std::vector<HostRange> known_;
+public:
+    PinnedLookup()
+    {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            get_ = reinterpret_cast<GetAttr>(fn);
+        else
+            cudaGetLastError();
+    }
+    // 0 = pageable; otherwise 1 + index of the allocation (stable for this object's lifetime)
+    int find(const void* p)
+    {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        for (size_t i = 0; i < known_.size(); ++i)
+            if (a >= known_[i].lo && a < known_[i].hi) return (int)i + 1;
+        HostRange r;
+        if (get_) {
+            CUmemorytype type{};
+            CUdeviceptr base = 0;
+            size_t size = 0;
+            if (get_(&type, CU_POINTER_ATTRIBUTE_MEMORY_TYPE, (CUdeviceptr)a) != CUDA_SUCCESS || type != CU_MEMORYTYPE_HOST) return 0;
+            if (get_(&base, CU_POINTER_ATTRIBUTE_RANGE_START_ADDR, (CUdeviceptr)a) != CUDA_SUCCESS ||
+                get_(&size, CU_POINTER_ATTRIBUTE_RANGE_SIZE, (CUdeviceptr)a) != CUDA_SUCCESS || size == 0) {
+                r.lo = a; r.hi = a + 1;            // pinned, extent unknown: never merged with anything
+            } else {
+                r.lo = (uintptr_t)base; r.hi = r.lo + size;
+            }
+        } else {
+            cudaPointerAttributes at{};
+            if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+            if (at.type != cudaMemoryTypeHost) return 0;
+            r.lo = a; r.hi = a + 1;
+        }
+        known_.push_back(r);
+        return (int)known_.size();
+    }
+};
 
 // Group jobs into frames and validate them; sangnom_plan.h derives for every processed plane how many
 // pool rows its pass must sweep and which blurred cost cells it hands to the next pass.
@@ -257,14 +313,15 @@ int launch_passes(sn_ctx* ctx, const std::vector<std::vector<sn::PlaneTask>>& by
 }
 
 // A run of bytes that is contiguous both in (pinned) host memory and in the device slot: one DMA transfer.
-struct Segment { char* host; char* dev; size_t bytes; };
+struct Segment { char* host; char* dev; size_t bytes; int alloc; };
 
-void add_segment(std::vector<Segment>& v, void* host, void* dev, size_t bytes)
+// alloc: which pinned allocation `host` lies in (runs are merged only inside one allocation)
+void add_segment(std::vector<Segment>& v, void* host, void* dev, size_t bytes, int alloc)
 {
     char* h = static_cast<char*>(host);
     char* d = static_cast<char*>(dev);
-    if (!v.empty() && v.back().host + v.back().bytes == h && v.back().dev + v.back().bytes == d) v.back().bytes += bytes;
-    else v.push_back(Segment{ h, d, bytes });
+    if (!v.empty() && v.back().alloc == alloc && v.back().host + v.back().bytes == h && v.back().dev + v.back().bytes == d) v.back().bytes += bytes;
+    else v.push_back(Segment{ h, d, bytes, alloc });
 }
 
 cudaError_t flush_segments(std::vector<Segment>& v, cudaMemcpyKind kind, cudaStream_t stream)
@@ -565,35 +622,57 @@ int sangnom_cuda_process_planes_device(sn_ctx* ctx, const sn_plane_job* jobs, in
     return SN_OK;
 }
 
+}  // extern "C"
+
 // ---------------------------------------------------------------------------------------------
-int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs)
+namespace {
+
+// Wait for every chunk of batches <= ticket (slots are drained oldest first) and forget finished batches.
+int drain_through(sn_ctx* ctx, uint64_t ticket)
 {
-    if (!ctx) return SN_ERR_INVALID;
-    if (njobs < 0 || (njobs > 0 && !jobs)) return ctx->fail(SN_ERR_INVALID, "bad job list");
-    if (njobs == 0) return SN_OK;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    int status = SN_OK;
+    for (int k = 0; k < kSlots; ++k) {
+        Slot& s = ctx->slots[(ctx->next_slot + k) % kSlots];
+        if (!s.busy || s.ticket > ticket) continue;
+        if (status == SN_OK) status = drain_slot(ctx, s);
+        else { cudaEventSynchronize(s.d2h_done); s.frames.clear(); s.busy = false; }
+    }
+    while (!ctx->batches.empty() && ctx->batches.front()->ticket <= ticket) ctx->batches.pop_front();
+    return status;
+}
+
+int submit_locked(sn_ctx* ctx, const sn_plane_job* user_jobs, int njobs, uint64_t* ticket_out)
+{
     SN_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     const int sb = ctx->sample_bytes;
 
-    std::vector<FramePlan> frames;
+    static const bool trace = getenv("SANGNOM_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    std::unique_ptr<Batch> batch(new Batch());
+    batch->ticket = ++ctx->last_ticket;
+    batch->jobs.assign(user_jobs, user_jobs + njobs);
+    const sn_plane_job* jobs = batch->jobs.data();
+    std::vector<FramePlan>& frames = batch->frames;
+    const uint64_t ticket = batch->ticket;
+    *ticket_out = ticket;
     int rc = plan_frames(ctx, jobs, njobs, false, frames);
     if (rc != SN_OK) return rc;
-
-    // classify host pointers once per distinct allocation is not possible in general; per job is fine
+    ctx->batches.push_back(std::move(batch));
+    PinnedLookup pinned;
     for (FramePlan& f : frames)
         for (Pass& p : f.passes) {
-            p.src_pinned = is_pinned_host(p.job->src);
-            p.dst_pinned = is_pinned_host(p.job->dst);
+            p.src_pinned = pinned.find(p.job->src);
+            p.dst_pinned = pinned.find(p.job->dst);
         }
 
+    const auto t_planned = std::chrono::steady_clock::now();
     cudaEventRecord(ctx->trace_base, ctx->h2d);
     const size_t chunk_frames = std::max<size_t>(1, (size_t)ctx->frames_in_flight / kSlots);
     size_t next = 0;
-    int slot_idx = 0;
     int status = SN_OK;
     while (next < frames.size() && status == SN_OK) {
-        Slot& s = ctx->slots[slot_idx];
-        slot_idx = (slot_idx + 1) % kSlots;
+        Slot& s = ctx->slots[ctx->next_slot];
+        ctx->next_slot = (ctx->next_slot + 1) % kSlots;
         if ((status = drain_slot(ctx, s)) != SN_OK) break;     // also guarantees the slot's device buffers are free
 
         const size_t first = next, last = std::min(frames.size(), next + chunk_frames);
@@ -662,9 +741,9 @@ int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs
                 if (p.up == Pass::STAGED) {
                     char* st = static_cast<char*>(s.stage_in.p) + p.stage_in_off;
                     for (int y = 0; y < p.n; ++y) std::memcpy(st + (size_t)y * p.src_pitch, kept + (size_t)y * kept_step, row);
-                    add_segment(up_segs, st, dsrc, p.src_bytes);
+                    add_segment(up_segs, st, dsrc, p.src_bytes, -1);                         // the slot's own staging buffer
                 } else if (p.up == Pass::LINEAR) {
-                    add_segment(up_segs, const_cast<void*>(jb.src), dsrc, p.src_bytes);
+                    add_segment(up_segs, const_cast<void*>(jb.src), dsrc, p.src_bytes, p.src_pinned);
                 } else {
                     e = flush_segments(up_segs, cudaMemcpyHostToDevice, ctx->h2d);          // keep submission order
                     if (e == cudaSuccess)
@@ -703,9 +782,9 @@ int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs
                 char* dplane_w = const_cast<char*>(dplane);
                 e = cudaSuccess;
                 if (p.down == Pass::STAGED)
-                    add_segment(down_segs, static_cast<char*>(s.stage_out.p) + p.stage_out_off, dplane_w, p.dst_pitch * p.H);
+                    add_segment(down_segs, static_cast<char*>(s.stage_out.p) + p.stage_out_off, dplane_w, p.dst_pitch * p.H, -1);
                 else if (p.down == Pass::LINEAR)
-                    add_segment(down_segs, jb.dst, dplane_w, row * p.H);
+                    add_segment(down_segs, jb.dst, dplane_w, row * p.H, p.dst_pinned);
                 else {
                     e = flush_segments(down_segs, cudaMemcpyDeviceToHost, ctx->d2h);
                     if (e == cudaSuccess)
@@ -720,16 +799,62 @@ int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs
         if (status != SN_OK) break;
         if ((e = cudaEventRecord(s.d2h_done, ctx->d2h)) != cudaSuccess) { status = ctx->cuda_fail(e, "event"); break; }
         s.busy = true;
+        s.ticket = ticket;
         ctx->stats.frames += last - first;
     }
-    // drain everything (in submission order) even on error so no copy is left writing user memory
-    for (int k = 0; k < kSlots; ++k) {
-        Slot& s = ctx->slots[(slot_idx + k) % kSlots];
-        if (status == SN_OK) status = drain_slot(ctx, s);
-        else { cudaEventSynchronize(s.d2h_done); s.frames.clear(); s.busy = false; }
+    if (trace) {
+        const auto t_end = std::chrono::steady_clock::now();
+        auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
+        fprintf(stderr, "[sangnom] submit of %d jobs: plan+classify %ld us, chunks (incl. waiting for slots) %ld us\n", njobs, us(t_begin, t_planned), us(t_planned, t_end));
     }
-    if (status != SN_OK) { cudaStreamSynchronize(ctx->h2d); cudaStreamSynchronize(ctx->d2h); cudaGetLastError(); }
+    if (status != SN_OK) {
+        // leave nothing in flight that writes user memory, then forget every batch
+        for (int k = 0; k < kSlots; ++k) {
+            Slot& s = ctx->slots[(ctx->next_slot + k) % kSlots];
+            if (s.busy) { cudaEventSynchronize(s.d2h_done); s.frames.clear(); s.busy = false; }
+        }
+        cudaStreamSynchronize(ctx->h2d); cudaStreamSynchronize(ctx->d2h); cudaGetLastError();
+        ctx->batches.clear();
+    }
     return status;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sangnom_cuda_submit(sn_ctx* ctx, const sn_plane_job* jobs, int njobs, sn_ticket* ticket)
+{
+    if (!ctx) return SN_ERR_INVALID;
+    if (!ticket) return ctx->fail(SN_ERR_INVALID, "null ticket pointer");
+    if (njobs < 0 || (njobs > 0 && !jobs)) return ctx->fail(SN_ERR_INVALID, "bad job list");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (njobs == 0) { *ticket = ctx->last_ticket; return SN_OK; }
+    uint64_t t = 0;
+    const int rc = submit_locked(ctx, jobs, njobs, &t);
+    *ticket = t;
+    return rc;
+}
+
+int sangnom_cuda_wait(sn_ctx* ctx, sn_ticket ticket)
+{
+    if (!ctx) return SN_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ticket > ctx->last_ticket) return ctx->fail(SN_ERR_INVALID, "unknown ticket");
+    SN_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    return drain_through(ctx, ticket);
+}
+
+int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs)
+{
+    if (!ctx) return SN_ERR_INVALID;
+    if (njobs < 0 || (njobs > 0 && !jobs)) return ctx->fail(SN_ERR_INVALID, "bad job list");
+    if (njobs == 0) return SN_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    uint64_t t = 0;
+    int rc = submit_locked(ctx, jobs, njobs, &t);
+    if (rc == SN_OK) rc = drain_through(ctx, t);
+    return rc;
 }
 
 }  // extern "C"

@@ -22,7 +22,7 @@ EXPORTS = [
     "sangnom_cuda_abi_version", "sangnom_cuda_create", "sangnom_cuda_destroy", "sangnom_cuda_process_planes",
     "sangnom_cuda_process_planes_device", "sangnom_cuda_synchronize", "sangnom_cuda_threshold",
     "sangnom_cuda_get_limits", "sangnom_cuda_get_stats", "sangnom_cuda_reset_stats", "sangnom_cuda_host_alloc",
-    "sangnom_cuda_host_free", "sangnom_cuda_last_error",
+    "sangnom_cuda_host_free", "sangnom_cuda_last_error", "sangnom_cuda_submit", "sangnom_cuda_wait",
 ]
 
 
@@ -70,6 +70,10 @@ def load():
     L.sangnom_cuda_destroy.argtypes = [C.c_void_p]
     L.sangnom_cuda_process_planes.restype = C.c_int
     L.sangnom_cuda_process_planes.argtypes = [C.c_void_p, C.POINTER(SnPlaneJob), C.c_int]
+    L.sangnom_cuda_submit.restype = C.c_int
+    L.sangnom_cuda_submit.argtypes = [C.c_void_p, C.POINTER(SnPlaneJob), C.c_int, C.POINTER(C.c_uint64)]
+    L.sangnom_cuda_wait.restype = C.c_int
+    L.sangnom_cuda_wait.argtypes = [C.c_void_p, C.c_uint64]
     L.sangnom_cuda_process_planes_device.restype = C.c_int
     L.sangnom_cuda_process_planes_device.argtypes = [C.c_void_p, C.POINTER(SnPlaneJob), C.c_int, C.c_void_p]
     L.sangnom_cuda_synchronize.restype = C.c_int
@@ -193,6 +197,16 @@ class Context:
     def process_jobs(self, jobs):
         arr = (SnPlaneJob * len(jobs))(*jobs)
         self._check(load().sangnom_cuda_process_planes(self._h, arr, len(jobs)))
+
+    def submit(self, jobs):
+        """Queue a batch (host buffers) and return its ticket; the buffers must stay alive until wait(ticket)."""
+        arr = jobs if isinstance(jobs, C.Array) else (SnPlaneJob * len(jobs))(*jobs)
+        t = C.c_uint64()
+        self._check(load().sangnom_cuda_submit(self._h, arr, len(arr), C.byref(t)))
+        return int(t.value)
+
+    def wait(self, ticket):
+        self._check(load().sangnom_cuda_wait(self._h, int(ticket)))
 
     def process_jobs_device(self, jobs, stream=None):
         """stream: a cudaStream_t handle as int (0 = CUDA's legacy default stream); None = the context's own stream."""

@@ -121,6 +121,15 @@ SN_API void sangnom_cuda_destroy(sn_ctx* ctx);
  * pipelined internally (H2D | kernels | D2H on separate streams, four chunks of frames in flight). */
 SN_API int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs);
 
+/* The same work split in two calls so that consecutive batches overlap (batch k+1 uploads while batch k
+ * downloads): submit queues the batch and returns a ticket - it blocks only while all chunk slots of the
+ * pipeline are occupied; wait returns when every dst of that batch (and of all earlier ones) is complete.
+ * The job array is copied; the src/dst BUFFERS must stay valid and untouched until wait returns.
+ * process_planes(jobs) == submit(jobs) + wait(ticket). An error in either call drains the whole pipeline. */
+typedef uint64_t sn_ticket;
+SN_API int sangnom_cuda_submit(sn_ctx* ctx, const sn_plane_job* jobs, int njobs, sn_ticket* ticket);
+SN_API int sangnom_cuda_wait(sn_ctx* ctx, sn_ticket ticket);
+
 /* DEVICE buffers: src/dst are device pointers on ctx's device. Asynchronous on `cuda_stream`, a
  * cudaStream_t passed as void* (NULL is CUDA's legacy default stream, as everywhere in CUDA;
  * SN_STREAM_CONTEXT selects the context's own compute stream); no host/device copies.

@@ -32,3 +32,44 @@ def test_host_path_matches_oracle(cuda, case):
     for i in range(nframes):
         assert_planes_equal(got[i], exp[i][:len(got[i])], f"{name} frame {i}")
     assert st["kernel_launches"] >= 1 or not (kw.get("luma", True) or kw.get("chroma", True))
+
+
+@pytest.mark.parametrize("pinned", [True, False], ids=["pinned", "pageable"])
+def test_overlapped_batches_submit_wait(cuda, pinned):
+    """sangnom_cuda_submit / _wait: three batches in flight at once (more chunks than pipeline slots), waited out of
+    submission order; every frame must equal the oracle and the synchronous call."""
+    from pysangnom.fakehost import FORMATS
+    from pysangnom.clips import make_frame
+    from oracle import oracle as O
+    fmt, w, h = FORMATS["YUV420P8"], 352, 288
+    nb, per = 3, 7
+    frames = [[make_frame(90 + b, w, h, fmt, "noise" if b % 2 else "edges", i) for i in range(per)] for b in range(nb)]
+    with cuda.Context(fmt.sample_bytes, w, h, max_frames_in_flight=8) as ctx:          # chunks of 2 frames
+        keep, tickets, outs = [], [], []
+        for b in range(nb):
+            jobs, dsts = [], []
+            for k, planes in enumerate(frames[b]):
+                if pinned:
+                    srcs = [cuda.pinned_empty(p.shape, p.dtype) for p in planes]
+                    for s_, p in zip(srcs, planes):
+                        s_[...] = p
+                    dd = [cuda.pinned_empty(p.shape, p.dtype) for p in planes]
+                else:
+                    srcs = [np.ascontiguousarray(p) for p in planes]
+                    dd = [np.empty_like(p) for p in planes]
+                for d in dd:
+                    d[...] = 0xEE
+                keep.append(srcs)
+                jobs += ctx.frame_jobs(srcs, dd, fmt.bits, order=0, aa=48, aac=48, parity=parity_of(k), frame_key=100 * b + k)
+                dsts.append(dd)
+            tickets.append(ctx.submit(jobs))
+            outs.append(dsts)
+        ctx.wait(tickets[1])            # implies batch 0
+        ctx.wait(tickets[0])            # already complete: returns at once
+        ctx.wait(tickets[2])
+        with pytest.raises(cuda.SangNomCudaError):
+            ctx.wait(tickets[2] + 5)
+    for b in range(nb):
+        for k, planes in enumerate(frames[b]):
+            exp = O.oracle_frame(planes, fmt.bits, order=0, aa=48, aac=48, parity=parity_of(k))
+            assert_planes_equal(outs[b][k], exp[:3], f"batch {b} frame {k}")
