@@ -123,6 +123,10 @@ struct sn_ctx {
     std::deque<std::unique_ptr<Batch>> batches;
     // device-entry resources
     DevBuf dev_state;
+    // persistent-pool mode (SN_FLAG_PERSISTENT_POOL): the pool state between frames, ping-pong
+    bool persistent = false;
+    DevBuf carry[2];
+    int carry_pos = 0;                   // carry[carry_pos] holds the state the next frame starts from
     DevBuf dev_tasks[kTaskRing];
     PinnedBuf dev_tasks_host[kTaskRing];
     cudaEvent_t dev_task_free[kTaskRing] = {};
@@ -247,15 +251,31 @@ int plan_frames(sn_ctx* ctx, const sn_plane_job* jobs, int njobs, bool device_en
         const int m = (int)f.passes.size();
         sn::PassGeometry geo[3];
         for (int q = 0; q < m; ++q) { geo[q] = sn::PassGeometry{}; geo[q].width = f.passes[q].W; geo[q].kept_rows = f.passes[q].n; }
-        f.state_bytes = sn::plan_frame_passes(geo, m, ctx->S, ctx->Hb, sb);
+        f.state_bytes = sn::plan_frame_passes(geo, m, ctx->S, ctx->Hb, sb, ctx->persistent);
         for (int q = 0; q < m; ++q) { f.passes[q].R = geo[q].sweep_rows; f.passes[q].in = geo[q].in; f.passes[q].out = geo[q].out; }
     }
     return SN_OK;
 }
 
-void place_state(FramePlan& f, char* base)
+// Resolve the frame's cost-state regions inside its scratch; in persistent-pool mode also hook the frame into the
+// chain of pool states (frames are placed in submission order, which is the order they run in).
+void place_state(sn_ctx* ctx, FramePlan& f, char* base)
 {
     for (Pass& p : f.passes) { sn::plan_place_state(p.in, base); sn::plan_place_state(p.out, base); }
+    if (ctx->persistent && !f.passes.empty() && ctx->carry[0].p) {
+        sn::plan_attach_carry(f.passes.front().in, f.passes.back().out, ctx->carry[ctx->carry_pos].p, ctx->carry[ctx->carry_pos ^ 1].p, ctx->Hb);
+        ctx->carry_pos ^= 1;
+    }
+}
+
+// Group the tasks of a set of frames into launches. Default: one launch per pass index over all frames (frames are
+// independent). Persistent pool: one launch per plane pass, frame after frame, because each frame reads the pool
+// state the previous one wrote.
+void add_task(const sn_ctx* ctx, std::vector<std::vector<sn::PlaneTask>>& launches, size_t q, const sn::PlaneTask& t)
+{
+    if (ctx->persistent) { launches.emplace_back(1, t); return; }
+    if (launches.size() <= q) launches.resize(q + 1);
+    launches[q].push_back(t);
 }
 
 sn::PlaneTask make_task(const sn_ctx* ctx, const Pass& p, void* plane, size_t pitch_bytes, const void* kept0, size_t kept_step_bytes)
@@ -480,6 +500,16 @@ int sangnom_cuda_create(const sn_config* cfg, sn_ctx** out)
     for (int i = 0; i < kTaskRing; ++i)
         if ((e = cudaEventCreateWithFlags(&ctx->dev_task_free[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&ctx->trace_base)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if (cfg->flags & SN_FLAG_PERSISTENT_POOL) {
+        ctx->persistent = true;
+        const size_t bytes = sn::plan_carry_bytes(S, Hb, cfg->sample_type);
+        for (DevBuf& c : ctx->carry)
+            if (bytes) {
+                if ((e = c.ensure(bytes)) != cudaSuccess) return bail(e, "pool state allocation");
+                if ((e = cudaMemset(c.p, 0, bytes)) != cudaSuccess) return bail(e, "cudaMemset");      // the zero-filled pool of a new instance
+            }
+        if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bail(e, "cudaDeviceSynchronize");
+    }
     *out = ctx;
     return SN_OK;
 }
@@ -501,6 +531,7 @@ void sangnom_cuda_destroy(sn_ctx* ctx)
         if (s.d2h_done) cudaEventDestroy(s.d2h_done);
     }
     ctx->dev_state.release();
+    for (DevBuf& c : ctx->carry) c.release();
     for (int i = 0; i < kTaskRing; ++i) {
         ctx->dev_tasks[i].release();
         ctx->dev_tasks_host[i].release();
@@ -574,11 +605,11 @@ int sangnom_cuda_process_planes_device(sn_ctx* ctx, const sn_plane_job* jobs, in
             SN_CUDA(ctx, cudaMemcpy2DAsync(c->dst, (size_t)c->dst_pitch, c->src, (size_t)c->src_pitch, (size_t)c->width * sb,
                                            (size_t)c->dst_height, cudaMemcpyDeviceToDevice, stream));
         }
-        place_state(f, static_cast<char*>(ctx->dev_state.p) + f.state_off);
+        place_state(ctx, f, static_cast<char*>(ctx->dev_state.p) + f.state_off);
     }
 
     const auto t2 = now();
-    std::vector<std::vector<sn::PlaneTask>> by_pass(3);
+    std::vector<std::vector<sn::PlaneTask>> by_pass;
     for (FramePlan& f : frames)
         for (size_t q = 0; q < f.passes.size(); ++q)
         {
@@ -589,7 +620,7 @@ int sangnom_cuda_process_planes_device(sn_ctx* ctx, const sn_plane_job* jobs, in
             if (jb.mode == SN_MODE_INPLACE) { kept0 = static_cast<const char*>(jb.dst) + (ptrdiff_t)jb.offset * jb.dst_pitch; step = 2 * (size_t)jb.dst_pitch; }
             else if (jb.mode == SN_MODE_FIELD) { kept0 = static_cast<const char*>(jb.src) + (ptrdiff_t)jb.offset * jb.src_pitch; step = 2 * (size_t)jb.src_pitch; }
             else { kept0 = static_cast<const char*>(jb.src); step = (size_t)jb.src_pitch; }
-            by_pass[q].push_back(make_task(ctx, p, jb.dst, (size_t)jb.dst_pitch, kept0, step));
+            add_task(ctx, by_pass, q, make_task(ctx, p, jb.dst, (size_t)jb.dst_pitch, kept0, step));
         }
     const auto t3 = now();
 
@@ -724,12 +755,12 @@ int submit_locked(sn_ctx* ctx, const sn_plane_job* user_jobs, int njobs, uint64_
 
         cudaEventRecord(s.h2d_start, ctx->h2d);
         // ---- upload (the reference's kept-field BitBlt, SangNom2.cpp:361-377, becomes DMA + the kernel's own reads) ----
-        std::vector<std::vector<sn::PlaneTask>> by_pass(3);
+        std::vector<std::vector<sn::PlaneTask>> by_pass;
         std::vector<Segment> up_segs, down_segs;
         for (size_t k = first; k < last && status == SN_OK; ++k) {
             FramePlan& f = frames[k];
             for (const sn_plane_job* c : f.copies) host_copy_plane(*c, sb);
-            place_state(f, static_cast<char*>(s.state.p) + f.state_off);
+            place_state(ctx, f, static_cast<char*>(s.state.p) + f.state_off);
             for (size_t q = 0; q < f.passes.size(); ++q) {
                 Pass& p = f.passes[q];
                 const sn_plane_job& jb = *p.job;
@@ -751,7 +782,7 @@ int submit_locked(sn_ctx* ctx, const sn_plane_job* user_jobs, int njobs, uint64_
                 }
                 if (e != cudaSuccess) { status = ctx->cuda_fail(e, "H2D copy"); break; }
                 ctx->stats.h2d_bytes += p.up == Pass::PITCHED ? row * p.n : p.src_bytes;
-                by_pass[q].push_back(make_task(ctx, p, static_cast<char*>(s.planes.p) + p.dst_off, p.dst_pitch, dsrc + p.src_first, p.src_step));
+                add_task(ctx, by_pass, q, make_task(ctx, p, static_cast<char*>(s.planes.p) + p.dst_off, p.dst_pitch, dsrc + p.src_first, p.src_step));
             }
         }
         if (status == SN_OK && (e = flush_segments(up_segs, cudaMemcpyHostToDevice, ctx->h2d)) != cudaSuccess) status = ctx->cuda_fail(e, "H2D copy");
@@ -759,15 +790,17 @@ int submit_locked(sn_ctx* ctx, const sn_plane_job* user_jobs, int njobs, uint64_
         // The task array rides the upload stream too: a small copy on the compute stream would queue on the
         // same DMA engine behind the NEXT chunks' bulk uploads and hold this chunk's kernels back.
         if ((status = upload_tasks(ctx, by_pass, static_cast<sn::PlaneTask*>(s.tasks_host.p), static_cast<sn::PlaneTask*>(s.tasks.p), ctx->h2d)) != SN_OK) break;
-        if ((e = cudaEventRecord(s.h2d_done, ctx->h2d)) != cudaSuccess || (e = cudaStreamWaitEvent(s.compute, s.h2d_done, 0)) != cudaSuccess) {
+        // persistent pool: every chunk's kernels on ONE stream, so that frames run in submission order across chunks
+        const cudaStream_t compute = ctx->persistent ? ctx->own_compute : s.compute;
+        if ((e = cudaEventRecord(s.h2d_done, ctx->h2d)) != cudaSuccess || (e = cudaStreamWaitEvent(compute, s.h2d_done, 0)) != cudaSuccess) {
             status = ctx->cuda_fail(e, "event"); break;
         }
 
         // ---- kernels ----
-        cudaEventRecord(s.k_start, s.compute);
-        status = launch_passes(ctx, by_pass, static_cast<sn::PlaneTask*>(s.tasks.p), s.compute);
+        cudaEventRecord(s.k_start, compute);
+        status = launch_passes(ctx, by_pass, static_cast<sn::PlaneTask*>(s.tasks.p), compute);
         if (status != SN_OK) break;
-        if ((e = cudaEventRecord(s.kernels_done, s.compute)) != cudaSuccess || (e = cudaStreamWaitEvent(ctx->d2h, s.kernels_done, 0)) != cudaSuccess) {
+        if ((e = cudaEventRecord(s.kernels_done, compute)) != cudaSuccess || (e = cudaStreamWaitEvent(ctx->d2h, s.kernels_done, 0)) != cudaSuccess) {
             status = ctx->cuda_fail(e, "event"); break;
         }
 

@@ -29,13 +29,17 @@ struct PassGeometry {
 inline size_t plan_align(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // passes[0..m) in processing order (Y,U,V). Returns the bytes of cost-state scratch the frame needs.
-inline size_t plan_frame_passes(PassGeometry* passes, int m, int S, int Hb, int sample_bytes)
+// persistent: the pool outlives the frame (one long-lived reference instance pulled sequentially): the last pass
+// must leave the whole pool as the reference's last processBuffers sweep does (rows 1..Hb-1, :133-136), so it - and
+// through the rule below every earlier pass - sweeps all pool rows; plan_attach_carry() wires the frame-to-frame state.
+inline size_t plan_frame_passes(PassGeometry* passes, int m, int S, int Hb, int sample_bytes, bool persistent = false)
 {
     for (int q = m - 1; q >= 0; --q) {
         PassGeometry& p = passes[q];
         p.in = CostState{};
         p.out = CostState{};
         p.sweep_rows = std::min(p.kept_rows - 1, Hb - 1);
+        if (persistent && q == m - 1) p.sweep_rows = std::max(p.sweep_rows, Hb - 1);
         if (q + 1 < m) p.sweep_rows = std::max(p.sweep_rows, std::min(Hb - 1, passes[q + 1].sweep_rows + 1));
     }
     size_t off = 0;
@@ -66,6 +70,17 @@ inline size_t plan_frame_passes(PassGeometry* passes, int m, int S, int Hb, int 
         passes[q + 1].in = st;
     }
     return off;
+}
+
+// Persistent pool: the state between frames is the whole pool, rows 1..Hb-1 x S columns of the nine buffers (row 0 and
+// row Hb are never written by the reference and stay zero). The first pass of a frame reads it wherever it has no
+// fresh raw costs of its own, the last pass writes it. Call after plan_place_state(); carry_in != carry_out.
+inline size_t plan_carry_bytes(int S, int Hb, int sample_bytes) { return Hb > 1 ? (size_t)kNumCost * (Hb - 1) * S * sample_bytes : 0; }
+inline void plan_attach_carry(CostState& first_in, CostState& last_out, void* carry_in, void* carry_out, int Hb)
+{
+    if (Hb <= 1) return;
+    first_in = CostState{ nullptr, carry_in, 0, 0, 1, Hb - 1 };
+    last_out = CostState{ nullptr, carry_out, 0, 0, 1, Hb - 1 };
 }
 
 inline void plan_place_state(CostState& s, char* base)

@@ -52,6 +52,10 @@ SangNom2::SangNom2(PClip _child, int order, int aa, int aac, int threads, bool d
     cfg.pool_height = vi.height;
     batch_frames_ = env_int("SANGNOM_B200_BATCH", 8, 1, 256);
     cfg.max_frames_in_flight = batch_frames_ < 3 ? 3 : batch_frames_;
+    // SANGNOM_B200_PERSISTENT=1: keep the scratch-pool state from frame to frame like one long-lived reference
+    // instance (bit-compatible with a sequential single-instance reference run where that is not frame-pure:
+    // widths that are not a multiple of 32, luma=false with subsampled chroma). Frames then run one after another.
+    if (env_int("SANGNOM_B200_PERSISTENT", 0, 0, 1)) cfg.flags |= SN_FLAG_PERSISTENT_POOL;
     if (sangnom_cuda_create(&cfg, &ctx_) != SN_OK)
         env->ThrowError("SangNom2: %s", sangnom_cuda_last_error(nullptr));
 }

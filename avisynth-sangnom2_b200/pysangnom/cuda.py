@@ -17,6 +17,7 @@ CUDA_LIB = os.path.join(_PKG_DIR, "libsangnom_cuda.so")
 SN_OK, SN_ERR_INVALID, SN_ERR_CUDA, SN_ERR_UNSUPPORTED, SN_ERR_NOMEM = range(5)
 MODE_COPY, MODE_FIELD, MODE_DH, MODE_INPLACE = range(4)
 ABI_VERSION = 1
+FLAG_PERSISTENT_POOL = 1
 
 EXPORTS = [
     "sangnom_cuda_abi_version", "sangnom_cuda_create", "sangnom_cuda_destroy", "sangnom_cuda_process_planes",
@@ -162,9 +163,9 @@ def make_job(src_ptr, src_pitch, dst_ptr, dst_pitch, width, dst_height, offset, 
 class Context:
     """sn_ctx wrapper. pool_width/pool_height are the OUTPUT luma dims (after dh)."""
 
-    def __init__(self, sample_bytes, pool_width, pool_height, device=0, max_frames_in_flight=0):
+    def __init__(self, sample_bytes, pool_width, pool_height, device=0, max_frames_in_flight=0, flags=0):
         L = load()
-        cfg = SnConfig(ABI_VERSION, device, sample_bytes, pool_width, pool_height, max_frames_in_flight, 0)
+        cfg = SnConfig(ABI_VERSION, device, sample_bytes, pool_width, pool_height, max_frames_in_flight, flags)
         h = C.c_void_p()
         rc = L.sangnom_cuda_create(C.byref(cfg), C.byref(h))
         if rc != SN_OK:

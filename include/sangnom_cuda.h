@@ -71,6 +71,15 @@ enum sn_mode {
     SN_MODE_INPLACE = 3      /* device entry only: dst already holds the kept field; src ignored (:393) */
 };
 
+/* sn_config.flags */
+/* Persistent scratch pool: frames are processed strictly in submission order and each frame starts from the pool
+ * state the previous frame left, exactly like ONE long-lived reference instance pulled sequentially (the reference
+ * never clears its pool, SangNom2.cpp:303-310). Matters only where the reference is not frame-pure: luma width not a
+ * multiple of 32 (the pad columns carry over) or luma=false with subsampled chroma. Frames become sequentially
+ * dependent, so this mode runs one plane pass at a time: use it for bit-compatibility with a sequential reference
+ * run, not for throughput. Default (0): every frame starts from a zero-filled pool (a fresh instance per frame). */
+#define SN_FLAG_PERSISTENT_POOL 1
+
 typedef struct sn_config {
     int abi_version;         /* SANGNOM_CUDA_ABI_VERSION */
     int device;              /* CUDA device ordinal */
@@ -78,7 +87,7 @@ typedef struct sn_config {
     int pool_width;          /* OUTPUT luma width in samples  (vi.width)            -> S  = align32 */
     int pool_height;         /* OUTPUT luma height in rows    (vi.height after dh)  -> Hb = (h+1)>>1 */
     int max_frames_in_flight;/* frames resident on the device at once (0 = library default) */
-    int flags;               /* reserved, 0 */
+    int flags;               /* SN_FLAG_* bits, 0 = defaults */
 } sn_config;
 
 /* One plane of one frame. Pitches are in BYTES. */

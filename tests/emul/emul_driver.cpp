@@ -15,17 +15,23 @@ extern "C" {
 // planes[i]: pointer to row 0; pitch in BYTES; returns 0, or -1 for unsupported geometry.
 int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long long* pitch_bytes, const void* const* srcs,
                const long long* src_pitch_bytes, const int* widths,
-               const int* heights, const int* offsets, const float* thresholds, int pool_width, int pool_height, int cluster)
+               const int* heights, const int* offsets, const float* thresholds, int pool_width, int pool_height, int cluster,
+               void* carry_in, void* carry_out)
 {
+    // carry_in/carry_out != NULL: persistent-pool mode, the pool state (plan_carry_bytes) before and after this frame
     const int S = (pool_width + 31) & ~31, Hb = (pool_height + 1) >> 1;
     sn::PassGeometry geo[3];
     for (int q = 0; q < nplanes; ++q) { geo[q] = sn::PassGeometry{}; geo[q].width = widths[q]; geo[q].kept_rows = heights[q] / 2; }
-    const size_t state_bytes = sn::plan_frame_passes(geo, nplanes, S, Hb, sample_bytes);
+    const bool persistent = carry_in != nullptr && carry_out != nullptr;
+    const size_t state_bytes = sn::plan_frame_passes(geo, nplanes, S, Hb, sample_bytes, persistent);
     std::vector<char> state(state_bytes + 256, (char)0x5A);      // poisoned: a read of a never-written cell is visible
     char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(state.data()) + 255) & ~(uintptr_t)255);
     for (int q = 0; q < nplanes; ++q) {
         sn::plan_place_state(geo[q].in, base);
         sn::plan_place_state(geo[q].out, base);
+    }
+    if (persistent && nplanes > 0) sn::plan_attach_carry(geo[0].in, geo[nplanes - 1].out, carry_in, carry_out, Hb);
+    for (int q = 0; q < nplanes; ++q) {
         sn::PlaneTask t{};
         t.plane = planes[q];
         t.pitch = pitch_bytes[q] / sample_bytes;
@@ -57,6 +63,11 @@ int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long lo
             emul::run_cluster(0, G, threads, sn::wide::smem_bytes<float>(seg), [&] { sn::wide::sangnom_wide_row_sweep<float, 1024, 1, true>(&t, g, seg); });
     }
     return 0;
+}
+
+size_t emul_carry_bytes(int sample_bytes, int pool_width, int pool_height)
+{
+    return sn::plan_carry_bytes((pool_width + 31) & ~31, (pool_height + 1) >> 1, sample_bytes);
 }
 
 }  // extern "C"

@@ -73,3 +73,59 @@ def test_overlapped_batches_submit_wait(cuda, pinned):
         for k, planes in enumerate(frames[b]):
             exp = O.oracle_frame(planes, fmt.bits, order=0, aa=48, aac=48, parity=parity_of(k))
             assert_planes_equal(outs[b][k], exp[:3], f"batch {b} frame {k}")
+
+
+PERSISTENT = [("cfg1_yv12_luma", "YV12", 720, 480, dict(order=1, aa=48, chroma=False), 5),
+              ("420p8_w100", "YUV420P8", 100, 48, dict(order=0, aa=48, aac=48), 6),
+              ("chroma_only", "YUV420P8", 720, 480, dict(luma=False, aa=48, aac=48), 4),
+              ("444p16_dh_w200", "YUV444P16", 200, 120, dict(dh=True, aa=48, aac=48), 4),
+              ("420ps_w332", "YUV420PS", 332, 244, dict(order=2, aa=48, aac=24), 4),
+              ("420p8_1080p_pure", "YUV420P8", 1920, 1080, dict(order=0, aa=48, aac=48), 2)]
+
+
+@pytest.mark.parametrize("entry", ["host", "device"])
+@pytest.mark.parametrize("case", PERSISTENT, ids=[c[0] for c in PERSISTENT])
+def test_persistent_pool_mode(cuda, case, entry):
+    """SN_FLAG_PERSISTENT_POOL: a clip pushed through ONE context in several calls equals the oracle run with one pool
+    for the whole clip (= a single long-lived reference instance pulled sequentially, tests/test_oracle.py pins that).
+    Chunks of 2 frames, two calls: the state crosses frames, chunks and calls."""
+    import torch
+    from oracle import oracle as O
+    from pysangnom.clips import make_frame
+    from pysangnom.fakehost import FORMATS
+    name, fmtname, w, h, kw, nframes = case
+    fmt = FORMATS[fmtname]
+    dh = kw.get("dh", False)
+    out_h = h * 2 if dh else h
+    frames = [make_frame(300 + len(name), w, h, fmt, "noise" if i % 3 else "edges", i) for i in range(nframes)]
+    pool = O.new_pool(w, out_h, fmt.sample_bytes)
+    args = dict(order=kw.get("order", 1), aa=kw.get("aa", 48), aac=kw.get("aac", 0), dh=dh, luma=kw.get("luma", True), chroma=kw.get("chroma", True))
+    exp = [O.oracle_frame(fr, fmt.bits, parity=parity_of(i), pool=pool, **args) for i, fr in enumerate(frames)]
+    got = []
+    with cuda.Context(fmt.sample_bytes, w, out_h, max_frames_in_flight=8, flags=cuda.FLAG_PERSISTENT_POOL) as ctx:
+        cut = nframes // 2 + 1
+        for lo, hi in ((0, cut), (cut, nframes)):
+            part = frames[lo:hi]
+            if entry == "host":
+                got += ctx.process_frames(part, fmt.bits, parities=[parity_of(i) for i in range(lo, hi)], **args)
+                continue
+            jobs, keep = [], []
+            for k, planes in enumerate(part):
+                off = cuda.resolve_offset(args["order"], parity_of(lo + k))
+                outs = []
+                for p, a in enumerate(planes[:3]):
+                    enabled = dh or (args["luma"] if p == 0 else args["chroma"])
+                    s_ = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(a.shape[0], -1)).cuda()
+                    d = torch.full((a.shape[0] * (2 if dh else 1), s_.shape[1]), 0xEE, dtype=torch.uint8, device="cuda")
+                    thr = cuda.threshold(args["aa"] if p == 0 else args["aac"], fmt.bits, fmt.sample_bytes)
+                    mode = cuda.MODE_DH if dh else (cuda.MODE_FIELD if enabled else cuda.MODE_COPY)
+                    jobs.append(cuda.make_job(s_.data_ptr(), s_.shape[1], d.data_ptr(), d.shape[1], a.shape[1], d.shape[0], off, mode, thr, p, lo + k))
+                    keep.append(s_)
+                    outs.append((d, a.dtype))
+                got.append(outs)
+            ctx.process_jobs_device(jobs)
+            ctx.synchronize()
+    if entry == "device":
+        got = [[d.cpu().numpy().view(dt).copy() for d, dt in fr] for fr in got]
+    for i in range(nframes):
+        assert_planes_equal(got[i][:3], exp[i][:3], f"persistent {name} {entry} frame {i}")

@@ -72,6 +72,22 @@ def test_same_calls_on_both_plugins(func, kw, fmtname):
         assert_planes_equal(got[i][:3], ref[i][:3], f"{func} {kw} {fmtname} frame {i}")
 
 
+@pytest.mark.skipif(O.reference_plugin_path() is None, reason="oracle/_ref not built")
+@pytest.mark.parametrize("fmtname,w,h,kw", [("YV12", 720, 480, dict(order=1, aa=48, chroma=False)), ("YV12", 176, 144, dict(luma=False, aa=48, aac=48)),
+                                            ("YUV420P10", 100, 48, dict(order=0, aa=48, aac=48)), ("YUV444PS", 100, 50, dict(dh=True, aa=48, aac=48))])
+def test_persistent_mode_equals_one_long_lived_reference_instance(monkeypatch, fmtname, w, h, kw):
+    """SANGNOM_B200_PERSISTENT=1: our plugin pulled sequentially == ONE reference instance (opt=0) pulled sequentially,
+    including the frames where that differs from a fresh instance (pad columns / chroma-only leftovers)."""
+    monkeypatch.setenv("SANGNOM_B200_PERSISTENT", "1")
+    monkeypatch.setenv("SANGNOM_B200_BATCH", "3")
+    fmt = FORMATS[fmtname]
+    frames = [make_frame(77, w, h, fmt, "noise", i) for i in range(7)]
+    ref = run_plugin(O.reference_plugin_path(), fmt, w, h, frames, dict(opt=0, **kw), fresh=False)
+    got = run_plugin(OURS, fmt, w, h, frames, kw, fresh=False)
+    for i in range(len(frames)):
+        assert_planes_equal(got[i][:3], ref[i][:3], f"persistent {fmtname} {kw} frame {i}")
+
+
 def test_legacy_semantics_without_reference():
     """SangNom(order=0) keeps the bottom field, (order=2) is double-rate; aac takes the script's opt."""
     fmt = FORMATS["YV12"]

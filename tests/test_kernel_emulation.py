@@ -27,14 +27,17 @@ def emul():
     L.emul_frame.restype = C.c_int
     L.emul_frame.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.POINTER(C.c_void_p),
                              C.POINTER(C.c_longlong), C.POINTER(C.c_int),
-                             C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int]
+                             C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.emul_carry_bytes.restype = C.c_size_t
+    L.emul_carry_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     return L
 
 
-def emulate(L, planes, bits, order=1, aa=48, aac=0, dh=False, luma=True, chroma=True, parity=True, cluster=1, out_of_place=False):
+def emulate(L, planes, bits, order=1, aa=48, aac=0, dh=False, luma=True, chroma=True, parity=True, cluster=1, out_of_place=False, carry=None):
     """Frame-level host logic in numpy (field placement, plane skipping), plane passes through the emulated kernel.
     out_of_place: the kept rows are handed to the kernel as a separate packed field buffer (what the host path
-    uploads) and the kernel writes them into the dst plane itself."""
+    uploads) and the kernel writes them into the dst plane itself.
+    carry: (in, out) numpy byte buffers of emul_carry_bytes() - persistent-pool mode."""
     off = cuda.resolve_offset(order, parity)
     sb = planes[0].dtype.itemsize
     outs, proc, fields = [], [], {}
@@ -63,7 +66,8 @@ def emulate(L, planes, bits, order=1, aa=48, aac=0, dh=False, luma=True, chroma=
                           (C.c_longlong * n)(*[outs[p].strides[0] for p in proc]), srcs, spitch, (C.c_int * n)(*[outs[p].shape[1] for p in proc]),
                           (C.c_int * n)(*[outs[p].shape[0] for p in proc]), (C.c_int * n)(*[off] * n),
                           (C.c_float * n)(*[cuda.threshold(aa if p == 0 else aac, bits, sb) for p in proc]),
-                          outs[0].shape[1], outs[0].shape[0], cluster)
+                          outs[0].shape[1], outs[0].shape[0], cluster,
+                          carry[0].ctypes.data if carry else None, carry[1].ctypes.data if carry else None)
         assert rc == 0
     return outs
 
@@ -115,3 +119,30 @@ def test_cluster_split_matches_oracle(emul, fmtname, w, h, kw, cluster):
     got = emulate(emul, fr, fmt.bits, cluster=cluster, **kw)
     exp = O.oracle_frame(fr, fmt.bits, **kw)
     assert_planes_equal(got, exp[:3], f"{fmtname} {w}x{h} {kw} G={cluster}")
+
+
+PERSISTENT_CASES = [("Y8", 40, 12, dict(order=1), 1), ("YV12", 100, 48, dict(order=0, aa=48, aac=48), 1), ("YV12", 72, 40, dict(luma=False, aa=48, aac=48), 1),
+                    ("YV12", 96, 64, dict(chroma=False), 1), ("YV24", 44, 20, dict(dh=True, aa=48, aac=48), 1), ("YUV420P16", 100, 40, dict(order=2, aa=48, aac=20), 1),
+                    ("Y32", 40, 12, dict(order=1), 1), ("YUV422PS", 68, 30, dict(order=1, aa=10, aac=30), 1), ("YV12", 250, 36, dict(order=0, aa=48, aac=48), 4),
+                    ("YV411", 72, 32, dict(order=1, aa=48, aac=30), 1)]
+
+
+@pytest.mark.parametrize("fmtname,w,h,kw,cluster", PERSISTENT_CASES, ids=[f"{c[0]}_{c[1]}x{c[2]}_{i}" for i, c in enumerate(PERSISTENT_CASES)])
+def test_persistent_pool_chain_matches_oracle(emul, fmtname, w, h, kw, cluster):
+    """Persistent-pool mode: four frames in sequence, each starting from the pool state the previous one left, against
+    the oracle run with one pool for the whole clip (= one long-lived reference instance, tests/test_oracle.py)."""
+    fmt = FORMATS[fmtname]
+    out_h = h * 2 if kw.get("dh") else h
+    pool = O.new_pool(w, out_h, fmt.sample_bytes)
+    nbytes = emul.emul_carry_bytes(fmt.sample_bytes, w, out_h)
+    carry = [np.zeros(max(nbytes, 1), np.uint8), np.zeros(max(nbytes, 1), np.uint8)]
+    differs_from_fresh = False
+    for i in range(4):
+        fr = make_frame(57, w, h, fmt, "noise" if i != 2 else "edges", i)
+        got = emulate(emul, fr, fmt.bits, parity=(i % 2 == 0), cluster=cluster, carry=(carry[i & 1], carry[(i & 1) ^ 1]), **kw)
+        exp = O.oracle_frame(fr, fmt.bits, parity=(i % 2 == 0), pool=pool, **kw)
+        assert_planes_equal(got, exp[:3], f"persistent {fmtname} {w}x{h} {kw} frame {i}")
+        fresh = O.oracle_frame(fr, fmt.bits, parity=(i % 2 == 0), **kw)
+        differs_from_fresh |= any(not np.array_equal(a, b) for a, b in zip(exp[:3], fresh[:3]))
+    if w % 32 != 0 and fmt.sample_bytes < 4:
+        assert differs_from_fresh, "case does not exercise the carried state"
