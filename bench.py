@@ -343,35 +343,59 @@ def run_ours(args):
     sync_s = time.perf_counter() - t0
     barrier()
     # (b) streaming: step i+1 is submitted before step i is waited for - how a frame server keeps the GPU fed
-    ectx.reset_stats()
-    tick = C.c_uint64()
-    pending = []
-    t0 = time.perf_counter()
-    for i in range(esteps):
-        arr = sets[i % 2][0]
-        check(lib.sangnom_cuda_submit(ectx._h, arr, len(arr), C.byref(tick)))
-        pending.append(int(tick.value))
-        if len(pending) == 2:
+    def stream(job_arrays):
+        ectx.reset_stats()
+        tick = C.c_uint64()
+        pending = []
+        t0 = time.perf_counter()
+        for i in range(esteps):
+            arr = job_arrays[i % 2]
+            check(lib.sangnom_cuda_submit(ectx._h, arr, len(arr), C.byref(tick)))
+            pending.append(int(tick.value))
+            if len(pending) == 2:
+                check(lib.sangnom_cuda_wait(ectx._h, pending.pop(0)))
+        while pending:
             check(lib.sangnom_cuda_wait(ectx._h, pending.pop(0)))
-    while pending:
-        check(lib.sangnom_cuda_wait(ectx._h, pending.pop(0)))
-    torch.cuda.synchronize()
-    e_s = time.perf_counter() - t0
-    est = ectx.stats()
-    t_e = torch.tensor([e_s, sync_s], dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, ectx.stats()
+
+    # spot-check an e2e output plane against the device-resident result of the same frame (same bytes expected)
+    def spot_check(what):
+        chk = sets[(esteps - 1) % 2][1][0]
+        ref_dev = dev_planes[0][:, :chk.shape[1] * sb].cpu().numpy().view(chk.dtype)
+        if proc[0] and not np.array_equal(ref_dev, chk):
+            raise RuntimeError(f"e2e output ({what}) differs from the device-resident output")
+        chk[...] = 0
+
+    e_s, est = stream([sets[0][0], sets[1][0]])
+    spot_check("frame input")
+    # (c) the same frames from a double-rate producer that hands over SEPARATED FIELDS: only the kept
+    # field exists on the host, so only it is uploaded (SN_MODE_DH, offset by field parity); output is identical.
+    field_s, fst = None, None
+    if all(proc[:nplanes]) and not kw.get("dh", False):
+        barrier()
+        fsets = []
+        for i in range(2):
+            farena = cuda.PinnedArena(Fe * (frame_bytes // 2 + 64) + 4096)
+            fjobs = []
+            for j, jb in enumerate(sets[i][0]):
+                a = base[(first + j // nplanes) % 4][j % nplanes]
+                f = farena.take((a.shape[0] // 2, a.shape[1]), a.dtype)
+                f[...] = a[jb.offset::2]
+                fjobs.append(cuda.make_job(f.ctypes.data, f.strides[0], jb.dst, jb.dst_pitch, jb.width, jb.dst_height, jb.offset,
+                                           cuda.MODE_DH, jb.threshold, jb.plane, jb.frame))
+            fsets.append(((cuda.SnPlaneJob * len(fjobs))(*fjobs), farena))
+        check(lib.sangnom_cuda_process_planes(ectx._h, fsets[1][0], len(fsets[1][0])))
+        field_s, fst = stream([fsets[0][0], fsets[1][0]])
+        spot_check("field input")
+    t_e = torch.tensor([e_s, sync_s, field_s or 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.barrier()
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = Fe * world * esteps / float(t_e[0].item())
     e2e_sync_value = Fe * world * esteps / float(t_e[1].item())
-    dst_host = sets[(esteps - 1) % 2][1]
+    e2e_field_value = Fe * world * esteps / float(t_e[2].item()) if field_s else None
     clocks = sampler.stop() if rank == 0 else None
-
-    # spot-check the e2e output against the device-resident result of the same frame (same bytes expected)
-    chk = dst_host[0]
-    ref_dev = dev_planes[0][:, :chk.shape[1] * sb].cpu().numpy().view(chk.dtype)
-    if proc[0] and not np.array_equal(ref_dev, chk):
-        raise RuntimeError("e2e output differs from the device-resident output")
 
     if rank == 0:
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -399,7 +423,10 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": est["h2d_bytes"] // esteps,
                     "d2h_bytes_per_step": est["d2h_bytes"] // esteps, "steps": esteps,
                     "api": "sangnom_cuda_submit/_wait, two steps in flight, pinned host arenas",
-                    "sync_call_value": e2e_sync_value},
+                    "sync_call_value": e2e_sync_value,
+                    "field_input": None if e2e_field_value is None else {
+                        "value": e2e_field_value, "h2d_bytes_per_step": fst["h2d_bytes"] // esteps, "d2h_bytes_per_step": fst["d2h_bytes"] // esteps,
+                        "note": "separated-field input (SN_MODE_DH): same output frames, half the upload"}},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

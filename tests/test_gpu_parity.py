@@ -129,3 +129,21 @@ def test_persistent_pool_mode(cuda, case, entry):
         got = [[d.cpu().numpy().view(dt).copy() for d, dt in fr] for fr in got]
     for i in range(nframes):
         assert_planes_equal(got[i][:3], exp[i][:3], f"persistent {name} {entry} frame {i}")
+
+
+def test_separated_fields_input(cuda):
+    """the double-rate producer hands over separated fields (SN_MODE_DH, offset by field parity): same
+    output frames as the woven input with order=0, half the upload."""
+    from oracle import oracle as O
+    from pysangnom.clips import make_frame
+    from pysangnom.fakehost import FORMATS
+    fmt, w, h = FORMATS["YUV420P8"], 352, 288
+    woven = [make_frame(12, w, h, fmt, "noise", i) for i in range(4)]
+    fields = [[p[cuda.resolve_offset(0, parity_of(i))::2] for p in fr] for i, fr in enumerate(woven)]
+    with cuda.Context(fmt.sample_bytes, w, h) as ctx:
+        got = ctx.process_frames(fields, fmt.bits, order=0, aa=48, aac=48, dh=True, parities=[parity_of(i) for i in range(4)])
+        st = ctx.stats()
+    for i, fr in enumerate(woven):
+        exp = O.oracle_frame(fr, fmt.bits, order=0, aa=48, aac=48, parity=parity_of(i))
+        assert_planes_equal(got[i][:3], exp[:3], f"fields frame {i}")
+    assert st["h2d_bytes"] * 2 <= st["d2h_bytes"] + 4 * 3 * 16 * 288      # staged rows are padded to 16 bytes
