@@ -55,6 +55,19 @@ int max_pool_width(int sample_bytes);
 cudaError_t launch_plane_tasks(int sample_bytes, const PlaneTask* tasks_dev, int ntasks, LaunchGeometry g,
                                cudaStream_t stream);
 
+// Quarter turns / transposition of whole planes (sangnom_turn.cuh), many planes per launch.
+struct TurnPlane {
+    const void* src; long long src_pitch;   // W x H samples, pitch in bytes
+    void* dst; long long dst_pitch;         // H x W samples
+    int width, height;
+};
+enum TurnKind { kTranspose = 0, kTurnRight = 1, kTurnLeft = 2 };
+// `tasks_dev`: device scratch of at least turn_task_bytes(n); `tasks_host`: pinned scratch of the same size that must
+// stay untouched until the copy queued on `stream` has run. Returns the launch error.
+size_t turn_task_bytes(int nplanes);
+cudaError_t launch_turn_planes(int sample_bytes, const TurnPlane* planes, int nplanes, TurnKind kind, void* tasks_host,
+                               void* tasks_dev, cudaStream_t stream);
+
 // Name of the kernel variant launch_plane_tasks would use (for logs / profiles).
 const char* kernel_variant_name(int sample_bytes, int S);
 

@@ -24,7 +24,10 @@ EXPORTS = [
     "sangnom_cuda_process_planes_device", "sangnom_cuda_synchronize", "sangnom_cuda_threshold",
     "sangnom_cuda_get_limits", "sangnom_cuda_get_stats", "sangnom_cuda_reset_stats", "sangnom_cuda_host_alloc",
     "sangnom_cuda_host_free", "sangnom_cuda_last_error", "sangnom_cuda_submit", "sangnom_cuda_wait",
+    "sangnom_cuda_chain_create", "sangnom_cuda_chain_destroy", "sangnom_cuda_chain_process", "sangnom_cuda_chain_get_stats",
+    "sangnom_cuda_chain_last_error", "sangnom_cuda_turn_planes_device",
 ]
+TURN_TRANSPOSE, TURN_RIGHT_LEFT, TURN_LEFT_RIGHT = range(3)
 
 
 class SnConfig(C.Structure):
@@ -36,6 +39,27 @@ class SnPlaneJob(C.Structure):
     _fields_ = [("src", C.c_void_p), ("src_pitch", C.c_ssize_t), ("dst", C.c_void_p), ("dst_pitch", C.c_ssize_t),
                 ("width", C.c_int), ("dst_height", C.c_int), ("offset", C.c_int), ("mode", C.c_int),
                 ("threshold", C.c_float), ("plane", C.c_int), ("frame", C.c_int)]
+
+
+class SnChainConfig(C.Structure):
+    _fields_ = [("abi_version", C.c_int), ("device", C.c_int), ("sample_type", C.c_int), ("width", C.c_int), ("height", C.c_int),
+                ("turn", C.c_int), ("max_frames_in_flight", C.c_int), ("flags", C.c_int)]
+
+
+class SnChainJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("src_pitch", C.c_ssize_t), ("dst", C.c_void_p), ("dst_pitch", C.c_ssize_t),
+                ("width", C.c_int), ("height", C.c_int), ("offset1", C.c_int), ("offset2", C.c_int),
+                ("threshold", C.c_float), ("plane", C.c_int), ("frame", C.c_int)]
+
+
+class SnChainStats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("pass_kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64), ("frames", C.c_uint64)]
+
+
+class SnTurnPlane(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("src_pitch", C.c_ssize_t), ("dst", C.c_void_p), ("dst_pitch", C.c_ssize_t),
+                ("width", C.c_int), ("height", C.c_int)]
 
 
 class SnLimits(C.Structure):
@@ -75,6 +99,18 @@ def load():
     L.sangnom_cuda_submit.argtypes = [C.c_void_p, C.POINTER(SnPlaneJob), C.c_int, C.POINTER(C.c_uint64)]
     L.sangnom_cuda_wait.restype = C.c_int
     L.sangnom_cuda_wait.argtypes = [C.c_void_p, C.c_uint64]
+    L.sangnom_cuda_chain_create.restype = C.c_int
+    L.sangnom_cuda_chain_create.argtypes = [C.POINTER(SnChainConfig), C.POINTER(C.c_void_p)]
+    L.sangnom_cuda_chain_destroy.restype = None
+    L.sangnom_cuda_chain_destroy.argtypes = [C.c_void_p]
+    L.sangnom_cuda_chain_process.restype = C.c_int
+    L.sangnom_cuda_chain_process.argtypes = [C.c_void_p, C.POINTER(SnChainJob), C.c_int]
+    L.sangnom_cuda_chain_get_stats.restype = C.c_int
+    L.sangnom_cuda_chain_get_stats.argtypes = [C.c_void_p, C.POINTER(SnChainStats)]
+    L.sangnom_cuda_chain_last_error.restype = C.c_char_p
+    L.sangnom_cuda_chain_last_error.argtypes = [C.c_void_p]
+    L.sangnom_cuda_turn_planes_device.restype = C.c_int
+    L.sangnom_cuda_turn_planes_device.argtypes = [C.c_int, C.c_int, C.POINTER(SnTurnPlane), C.c_int, C.c_void_p]
     L.sangnom_cuda_process_planes_device.restype = C.c_int
     L.sangnom_cuda_process_planes_device.argtypes = [C.c_void_p, C.POINTER(SnPlaneJob), C.c_int, C.c_void_p]
     L.sangnom_cuda_synchronize.restype = C.c_int
@@ -258,6 +294,64 @@ class Context:
             keep.append(srcs)
             par = True if parities is None else parities[k]
             jobs += self.frame_jobs(srcs, dsts, bits, order, aa, aac, dh, luma, chroma, par, frame_key=k)
+            outs.append(dsts)
+        self.process_jobs(jobs)
+        return outs
+
+
+class Chain:
+    """sn_chain wrapper: SangNom2(dh=true) -> turn -> SangNom2(dh=true) -> turn back on the device.
+    width/height: INPUT luma size; every frame comes back as 2*width x 2*height."""
+
+    def __init__(self, sample_bytes, width, height, turn=TURN_TRANSPOSE, device=0, max_frames_in_flight=0):
+        L = load()
+        cfg = SnChainConfig(ABI_VERSION, device, sample_bytes, width, height, turn, max_frames_in_flight, 0)
+        h = C.c_void_p()
+        rc = L.sangnom_cuda_chain_create(C.byref(cfg), C.byref(h))
+        if rc != SN_OK:
+            raise SangNomCudaError(rc, L.sangnom_cuda_chain_last_error(None).decode())
+        self._h = h
+        self.sample_bytes = sample_bytes
+
+    def close(self):
+        if self._h:
+            load().sangnom_cuda_chain_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def process_jobs(self, jobs):
+        arr = jobs if isinstance(jobs, C.Array) else (SnChainJob * len(jobs))(*jobs)
+        rc = load().sangnom_cuda_chain_process(self._h, arr, len(arr))
+        if rc != SN_OK:
+            raise SangNomCudaError(rc, load().sangnom_cuda_chain_last_error(self._h).decode())
+
+    def stats(self):
+        s = SnChainStats()
+        load().sangnom_cuda_chain_get_stats(self._h, C.byref(s))
+        return {k: int(getattr(s, k)) for k, _ in SnChainStats._fields_}
+
+    def process_frames(self, frames, bits, aa=48, aac=0, offset1=0, offset2=0):
+        """frames: list of plane lists (numpy, Y[,U,V]). Returns the 2W x 2H output planes per frame."""
+        outs, jobs, keep = [], [], []
+        for k, planes in enumerate(frames):
+            srcs = [np.ascontiguousarray(p) for p in planes[:3]]
+            dsts = [np.empty((2 * p.shape[0], 2 * p.shape[1]), dtype=p.dtype) for p in srcs]
+            keep.append(srcs)
+            for p, (s_, d) in enumerate(zip(srcs, dsts)):
+                thr = threshold(aa if p == 0 else aac, bits, self.sample_bytes)
+                jobs.append(SnChainJob(s_.ctypes.data, s_.strides[0], d.ctypes.data, d.strides[0], s_.shape[1], s_.shape[0],
+                                       offset1, offset2, thr, p, k))
             outs.append(dsts)
         self.process_jobs(jobs)
         return outs

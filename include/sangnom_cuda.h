@@ -161,6 +161,63 @@ SN_API void sangnom_cuda_reset_stats(sn_ctx* ctx);
 SN_API void* sangnom_cuda_host_alloc(size_t bytes);
 SN_API void sangnom_cuda_host_free(void* p);
 
+/* ---- Anti-aliasing chain: SangNom2(dh=true) -> turn -> SangNom2(dh=true) -> turn back, on the device ----------
+ * What scripts build from four filters around the reference (README.md:43-46 `dh`; AviSynth TurnRight/TurnLeft or
+ * VapourSynth std.Transpose between the two calls): a W x H frame becomes 2W x 2H. Here the frame is uploaded once,
+ * stays in device memory across both passes and both turns, and is downloaded once. Each pass is bit-identical to
+ * a stand-alone SangNom2(dh=true) call on the (turned) clip; planes of a frame share a pool per pass as usual. */
+typedef struct sn_chain sn_chain;
+
+#define SN_TURN_TRANSPOSE  0   /* transpose, pass, transpose */
+#define SN_TURN_RIGHT_LEFT 1   /* TurnRight (clockwise), pass, TurnLeft */
+#define SN_TURN_LEFT_RIGHT 2   /* TurnLeft, pass, TurnRight */
+
+typedef struct sn_chain_config {
+    int abi_version;          /* SANGNOM_CUDA_ABI_VERSION */
+    int device;
+    int sample_type;          /* SN_SAMPLE_* */
+    int width, height;        /* INPUT luma size */
+    int turn;                 /* SN_TURN_* */
+    int max_frames_in_flight; /* 0 = default */
+    int flags;                /* reserved, 0 */
+} sn_chain_config;
+
+typedef struct sn_chain_job {
+    const void* src;          /* host, W x H samples of one plane */
+    ptrdiff_t src_pitch;      /* bytes */
+    void* dst;                /* host, 2W x 2H samples */
+    ptrdiff_t dst_pitch;
+    int width, height;        /* W, H of this plane */
+    int offset1, offset2;     /* field offset (0 keep as top rows, 1 as bottom rows) of pass 1 / pass 2 - what
+                                 order/parity resolve to in the two SangNom2 calls */
+    float threshold;          /* sangnom_cuda_threshold(aa or aac, ...) - both passes */
+    int plane;                /* 0 Y, 1 U, 2 V */
+    int frame;                /* caller's frame key */
+} sn_chain_job;
+
+typedef struct sn_chain_stats {
+    uint64_t kernel_launches;       /* turn kernels */
+    uint64_t pass_kernel_launches;  /* row-sweep kernels of both passes */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t frames;
+} sn_chain_stats;
+
+SN_API int sangnom_cuda_chain_create(const sn_chain_config* cfg, sn_chain** out);
+SN_API void sangnom_cuda_chain_destroy(sn_chain* chain);
+/* Synchronous; frames are pipelined internally (upload | passes + turns | download). */
+SN_API int sangnom_cuda_chain_process(sn_chain* chain, const sn_chain_job* jobs, int njobs);
+SN_API int sangnom_cuda_chain_get_stats(sn_chain* chain, sn_chain_stats* out);
+SN_API const char* sangnom_cuda_chain_last_error(sn_chain* chain);
+
+/* The turn on its own, device planes: dst (height x width samples) = src (width x height) transposed (kind 0),
+ * turned clockwise (1) or counter-clockwise (2). Synchronous with respect to `cuda_stream`. */
+typedef struct sn_turn_plane {
+    const void* src; ptrdiff_t src_pitch;
+    void* dst; ptrdiff_t dst_pitch;
+    int width, height;        /* of src, in samples */
+} sn_turn_plane;
+SN_API int sangnom_cuda_turn_planes_device(int sample_type, int kind, const sn_turn_plane* planes, int nplanes, void* cuda_stream);
+
 /* Last error text of ctx (or of the calling thread's last failed create when ctx == NULL). */
 SN_API const char* sangnom_cuda_last_error(sn_ctx* ctx);
 SN_API int sangnom_cuda_abi_version(void);

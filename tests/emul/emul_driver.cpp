@@ -6,6 +6,7 @@
 #include "sangnom_plan.h"
 #include "sangnom_u8.cuh"
 #include "sangnom_wide.cuh"
+#include "sangnom_turn.cuh"
 
 #include <cstdio>
 
@@ -61,6 +62,27 @@ int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long lo
             emul::run_cluster(0, G, threads, sn::wide::smem_bytes<uint16_t>(seg), [&] { sn::wide::sangnom_wide_row_sweep<uint16_t, 1024, 1, true>(&t, g, seg); });
         else
             emul::run_cluster(0, G, threads, sn::wide::smem_bytes<float>(seg), [&] { sn::wide::sangnom_wide_row_sweep<float, 1024, 1, true>(&t, g, seg); });
+    }
+    return 0;
+}
+
+// One plane through the turn kernel (sangnom_turn.cuh): kind 0 transpose, 1 clockwise, 2 counter-clockwise.
+int emul_turn(int sample_bytes, int kind, const void* src, long long src_pitch, void* dst, long long dst_pitch, int width, int height)
+{
+    const int TS = sn::turn::tile_side(sample_bytes);
+    sn::turn::TurnTask t{};
+    t.src = src; t.dst = dst; t.src_pitch = src_pitch; t.dst_pitch = dst_pitch; t.width = width; t.height = height;
+    t.tiles_x = (width + TS - 1) / TS;
+    t.first_block = 0;
+    const int blocks = t.tiles_x * ((height + TS - 1) / TS);
+    const int fr = kind == 2, fc = kind == 1;
+    for (int b = 0; b < blocks; ++b) {
+        auto body = [&] {
+            if (sample_bytes == 1) sn::turn::sangnom_turn_planes<1>(&t, 1, fr, fc);
+            else if (sample_bytes == 2) sn::turn::sangnom_turn_planes<2>(&t, 1, fr, fc);
+            else sn::turn::sangnom_turn_planes<4>(&t, 1, fr, fc);
+        };
+        emul::run_block((unsigned)b, sn::turn::kThreads, sn::turn::smem_bytes(sample_bytes), body);
     }
     return 0;
 }

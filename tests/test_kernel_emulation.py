@@ -146,3 +146,19 @@ def test_persistent_pool_chain_matches_oracle(emul, fmtname, w, h, kw, cluster):
         differs_from_fresh |= any(not np.array_equal(a, b) for a, b in zip(exp[:3], fresh[:3]))
     if w % 32 != 0 and fmt.sample_bytes < 4:
         assert differs_from_fresh, "case does not exercise the carried state"
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.float32], ids=["u8", "u16", "f32"])
+@pytest.mark.parametrize("w,h", [(128, 128), (256, 128), (130, 70), (64, 200), (7, 5)])
+@pytest.mark.parametrize("kind", [0, 1, 2], ids=["transpose", "right", "left"])
+def test_turn_kernel(emul, dtype, w, h, kind):
+    """sangnom_turn.cuh (AA chain): transpose / TurnRight / TurnLeft of a plane, whole tiles (word path with in-register
+    cell transposition) and ragged edges (sample path)."""
+    emul.emul_turn.restype = C.c_int
+    emul.emul_turn.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int]
+    rng = np.random.default_rng(w * 1000 + h)
+    a = rng.integers(0, 250, size=(h, w)).astype(dtype)
+    out = np.zeros((w, h), dtype=dtype)
+    assert emul.emul_turn(a.itemsize, kind, a.ctypes.data, a.strides[0], out.ctypes.data, out.strides[0], w, h) == 0
+    exp = [a.T, np.rot90(a, -1), np.rot90(a, 1)][kind]
+    assert np.array_equal(out, exp)
