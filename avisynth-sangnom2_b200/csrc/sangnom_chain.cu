@@ -42,7 +42,6 @@ constexpr int kChainSlots = 3;
 
 struct ChainSlot {
     Buf src, mid1, mid2, mid3, out;         // W x H | W x 2H | 2H x W | 2H x 2W | 2W x 2H, all planes of the chunk
-    Buf turn_dev[2], turn_host[2];
     cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
     bool busy = false;
 };
@@ -92,7 +91,6 @@ void sangnom_cuda_chain_destroy(sn_chain* ch)
     cudaDeviceSynchronize();
     for (ChainSlot& s : ch->slots) {
         s.src.release(); s.mid1.release(); s.mid2.release(); s.mid3.release(); s.out.release();
-        for (int k = 0; k < 2; ++k) { s.turn_dev[k].release(); s.turn_host[k].release(); }
         if (s.h2d_done) cudaEventDestroy(s.h2d_done);
         if (s.compute_done) cudaEventDestroy(s.compute_done);
         if (s.d2h_done) cudaEventDestroy(s.d2h_done);
@@ -139,15 +137,15 @@ int sangnom_cuda_chain_create(const sn_chain_config* cfg, sn_chain** out)
     if ((e = cudaStreamCreateWithFlags(&ch->d2h, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&ch->compute, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     for (ChainSlot& s : ch->slots) {
-        for (int k = 0; k < 2; ++k) s.turn_host[k].pinned = true;
         if ((e = cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
         if ((e = cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
         if ((e = cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     }
-    // frames per chunk: default keeps about 8 GB of device memory in the three slots (a frame occupies
-    // 1 + 2 + 2 + 4 + 4 = 13 times its input size)
+    // frames per chunk: a chunk has to fill the GPU with row-sweep blocks on its own (the passes of a chunk are
+    // latency-bound: H or W sequential rows), i.e. about 50 frames of 3 planes; the default keeps at most ~36 GB of
+    // device memory in the three slots (a frame occupies 1 + 2 + 2 + 4 + 4 = 13 times its input size)
     const double per_frame = 13.0 * 3.0 * (double)cfg->width * cfg->height * cfg->sample_type;
-    const int total = cfg->max_frames_in_flight > 0 ? cfg->max_frames_in_flight : (int)std::max(3.0, std::min(96.0, 8.0e9 / per_frame));
+    const int total = cfg->max_frames_in_flight > 0 ? cfg->max_frames_in_flight : (int)std::max(3.0, std::min(150.0, 36.0e9 / per_frame));
     ch->frames_per_chunk = std::max(1, total / kChainSlots);
     *out = ch;
     return SN_OK;
@@ -233,12 +231,6 @@ int sangnom_cuda_chain_process(sn_chain* ch, const sn_chain_job* jobs, int njobs
             status = ch->fail(SN_ERR_CUDA, "chain slot allocation: %s", cudaGetErrorString(e));
             break;
         }
-        for (int k = 0; k < 2; ++k)
-            if ((e = s.turn_dev[k].ensure(sn::turn_task_bytes(np))) != cudaSuccess || (e = s.turn_host[k].ensure(sn::turn_task_bytes(np))) != cudaSuccess) {
-                status = ch->fail(SN_ERR_CUDA, "chain slot allocation: %s", cudaGetErrorString(e));
-                break;
-            }
-        if (status != SN_OK) break;
         char* const d_src = static_cast<char*>(s.src.p);
         char* const d1 = static_cast<char*>(s.mid1.p);
         char* const d2 = static_cast<char*>(s.mid2.p);
@@ -277,7 +269,8 @@ int sangnom_cuda_chain_process(sn_chain* ch, const sn_chain_job* jobs, int njobs
             const Place& p = pl[i];
             tp[i] = sn::TurnPlane{ d1 + p.o1, (long long)p.p1, d2 + p.o2, (long long)p.p2, p.jb->width, 2 * p.jb->height };
         }
-        if ((e = sn::launch_turn_planes(sb, tp.data(), np, first_turn, s.turn_host[0].p, s.turn_dev[0].p, ch->compute)) != cudaSuccess) {
+        int nl = 0;
+        if ((e = sn::launch_turn_planes(sb, tp.data(), np, first_turn, ch->compute, &nl)) != cudaSuccess) {
             status = ch->fail(SN_ERR_CUDA, "turn: %s", cudaGetErrorString(e)); break;
         }
         // ---- pass 2: 2H x W -> 2H x 2W ----
@@ -297,10 +290,11 @@ int sangnom_cuda_chain_process(sn_chain* ch, const sn_chain_job* jobs, int njobs
             const Place& p = pl[i];
             tp[i] = sn::TurnPlane{ d3 + p.o3, (long long)p.p3, d_out + p.o_out, (long long)p.p_out, 2 * p.jb->height, 2 * p.jb->width };
         }
-        if ((e = sn::launch_turn_planes(sb, tp.data(), np, second_turn, s.turn_host[1].p, s.turn_dev[1].p, ch->compute)) != cudaSuccess) {
+        ch->stats.kernel_launches += nl;
+        if ((e = sn::launch_turn_planes(sb, tp.data(), np, second_turn, ch->compute, &nl)) != cudaSuccess) {
             status = ch->fail(SN_ERR_CUDA, "turn: %s", cudaGetErrorString(e)); break;
         }
-        ch->stats.kernel_launches += 2;            // the two turn launches; the passes count in their own contexts
+        ch->stats.kernel_launches += nl;           // turn launches; the passes count in their own contexts
         if ((e = cudaEventRecord(s.compute_done, ch->compute)) != cudaSuccess || (e = cudaStreamWaitEvent(ch->d2h, s.compute_done, 0)) != cudaSuccess) {
             status = ch->fail(SN_ERR_CUDA, "event: %s", cudaGetErrorString(e)); break;
         }
@@ -336,23 +330,10 @@ int sangnom_cuda_turn_planes_device(int sample_type, int kind, const sn_turn_pla
 {
     if (nplanes < 0 || (nplanes > 0 && !planes) || kind < 0 || kind > 2) return SN_ERR_INVALID;
     if (nplanes == 0) return SN_OK;
-    // scratch for the task array: allocated per call and released after the stream has consumed it (this entry is a
-    // convenience for tests and for callers that chain the device entries themselves; the chain object keeps its own)
-    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
-    void *host = nullptr, *dev = nullptr;
-    const size_t bytes = sn::turn_task_bytes(nplanes);
-    if (cudaHostAlloc(&host, bytes, cudaHostAllocDefault) != cudaSuccess || cudaMalloc(&dev, bytes) != cudaSuccess) {
-        if (host) cudaFreeHost(host);
-        cudaGetLastError();
-        return SN_ERR_NOMEM;
-    }
     std::vector<sn::TurnPlane> tp((size_t)nplanes);
     for (int i = 0; i < nplanes; ++i)
         tp[i] = sn::TurnPlane{ planes[i].src, (long long)planes[i].src_pitch, planes[i].dst, (long long)planes[i].dst_pitch, planes[i].width, planes[i].height };
-    cudaError_t e = sn::launch_turn_planes(sample_type, tp.data(), nplanes, static_cast<sn::TurnKind>(kind), host, dev, stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    cudaFreeHost(host);
-    cudaFree(dev);
+    const cudaError_t e = sn::launch_turn_planes(sample_type, tp.data(), nplanes, static_cast<sn::TurnKind>(kind), static_cast<cudaStream_t>(cuda_stream));
     if (e != cudaSuccess) { cudaGetLastError(); return SN_ERR_CUDA; }
     return SN_OK;
 }

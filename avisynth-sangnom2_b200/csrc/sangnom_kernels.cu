@@ -122,38 +122,39 @@ const char* kernel_variant_name(int sample_bytes, int S)
     }
 }
 
-size_t turn_task_bytes(int nplanes) { return (size_t)std::max(nplanes, 1) * sizeof(turn::TurnTask); }
-
-cudaError_t launch_turn_planes(int sample_bytes, const TurnPlane* planes, int nplanes, TurnKind kind, void* tasks_host,
-                               void* tasks_dev, cudaStream_t stream)
+cudaError_t launch_turn_planes(int sample_bytes, const TurnPlane* planes, int nplanes, TurnKind kind, cudaStream_t stream, int* launches)
 {
+    if (launches) *launches = 0;
     if (nplanes <= 0) return cudaSuccess;
     if (sample_bytes != 1 && sample_bytes != 2 && sample_bytes != 4) return cudaErrorInvalidValue;
-    turn::TurnTask* host = static_cast<turn::TurnTask*>(tasks_host);
     const int TS = turn::tile_side(sample_bytes);
-    int blocks = 0;
-    for (int i = 0; i < nplanes; ++i) {
-        const TurnPlane& p = planes[i];
-        if (p.width <= 0 || p.height <= 0) return cudaErrorInvalidValue;
-        turn::TurnTask t{};
-        t.src = p.src; t.dst = p.dst; t.src_pitch = p.src_pitch; t.dst_pitch = p.dst_pitch;
-        t.width = p.width; t.height = p.height;
-        t.tiles_x = (p.width + TS - 1) / TS;
-        t.first_block = blocks;
-        blocks += t.tiles_x * ((p.height + TS - 1) / TS);
-        host[i] = t;
-    }
-    cudaError_t e = cudaMemcpyAsync(tasks_dev, host, (size_t)nplanes * sizeof(turn::TurnTask), cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess) return e;
     const int fr = kind == kTurnLeft, fc = kind == kTurnRight;
-    const turn::TurnTask* dev = static_cast<const turn::TurnTask*>(tasks_dev);
     const size_t smem = turn::smem_bytes(sample_bytes);
-    switch (sample_bytes) {
-        case 1: turn::sangnom_turn_planes<1><<<blocks, turn::kThreads, smem, stream>>>(dev, nplanes, fr, fc); break;
-        case 2: turn::sangnom_turn_planes<2><<<blocks, turn::kThreads, smem, stream>>>(dev, nplanes, fr, fc); break;
-        default: turn::sangnom_turn_planes<4><<<blocks, turn::kThreads, smem, stream>>>(dev, nplanes, fr, fc); break;
+    for (int first = 0; first < nplanes; first += turn::kMaxTasks) {
+        const int n = std::min(turn::kMaxTasks, nplanes - first);
+        turn::TurnBatch batch{};
+        int tiles = 0;
+        for (int i = 0; i < n; ++i) {
+            const TurnPlane& p = planes[first + i];
+            if (p.width <= 0 || p.height <= 0) return cudaErrorInvalidValue;
+            turn::TurnTask& t = batch.t[i];
+            t.src = p.src; t.dst = p.dst; t.src_pitch = p.src_pitch; t.dst_pitch = p.dst_pitch;
+            t.width = p.width; t.height = p.height;
+            t.tiles_x = (p.width + TS - 1) / TS;
+            t.first_block = tiles;
+            tiles += t.tiles_x * ((p.height + TS - 1) / TS);
+        }
+        const int blocks = (tiles + turn::kTilesPerBlock - 1) / turn::kTilesPerBlock;
+        switch (sample_bytes) {
+            case 1: turn::sangnom_turn_planes<1><<<blocks, turn::kThreads, smem, stream>>>(batch, n, tiles, fr, fc); break;
+            case 2: turn::sangnom_turn_planes<2><<<blocks, turn::kThreads, smem, stream>>>(batch, n, tiles, fr, fc); break;
+            default: turn::sangnom_turn_planes<4><<<blocks, turn::kThreads, smem, stream>>>(batch, n, tiles, fr, fc); break;
+        }
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (launches) ++*launches;
     }
-    return cudaGetLastError();
+    return cudaSuccess;
 }
 
 cudaError_t launch_plane_tasks(int sample_bytes, const PlaneTask* tasks_dev, int ntasks, LaunchGeometry g, cudaStream_t stream)

@@ -62,11 +62,9 @@ struct TurnPlane {
     int width, height;
 };
 enum TurnKind { kTranspose = 0, kTurnRight = 1, kTurnLeft = 2 };
-// `tasks_dev`: device scratch of at least turn_task_bytes(n); `tasks_host`: pinned scratch of the same size that must
-// stay untouched until the copy queued on `stream` has run. Returns the launch error.
-size_t turn_task_bytes(int nplanes);
-cudaError_t launch_turn_planes(int sample_bytes, const TurnPlane* planes, int nplanes, TurnKind kind, void* tasks_host,
-                               void* tasks_dev, cudaStream_t stream);
+// Asynchronous on `stream`; the plane table travels in the kernel parameters (64 planes per launch). Returns the
+// launch error; *launches (optional) receives the number of kernels launched.
+cudaError_t launch_turn_planes(int sample_bytes, const TurnPlane* planes, int nplanes, TurnKind kind, cudaStream_t stream, int* launches = nullptr);
 
 // Name of the kernel variant launch_plane_tasks would use (for logs / profiles).
 const char* kernel_variant_name(int sample_bytes, int S);

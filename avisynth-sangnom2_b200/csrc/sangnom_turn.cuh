@@ -15,6 +15,13 @@
 #pragma once
 #include <stdint.h>
 
+#ifndef SN_GRID_CONSTANT
+#ifdef SN_HOST_EMULATION
+#define SN_GRID_CONSTANT
+#else
+#define SN_GRID_CONSTANT __grid_constant__
+#endif
+#endif
 #ifndef SN_DYNAMIC_SMEM
 #define SN_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
@@ -31,6 +38,9 @@ struct TurnTask {
     int tiles_x;            // tiles per tile row of this task
     int first_block;        // index of the task's first tile in the launch
 };
+
+constexpr int kMaxTasks = 64;           // planes per launch: the task table travels as a kernel parameter (3 KB)
+struct TurnBatch { TurnTask t[kMaxTasks]; };
 
 constexpr int kThreads = 256;           // 32 x 8
 inline __host__ __device__ int tile_side(int sample_bytes) { return 32 * (4 / sample_bytes); }     // samples
@@ -65,73 +75,123 @@ template <int kBytes> __device__ __forceinline__ uint32_t reverse_samples(uint32
     else return prmt(w, 0u, 0x0123);
 }
 
-// One launch serves many planes: block b belongs to the task whose [first_block, first_block + tiles) range holds it.
+constexpr int kBandRows = 16;
+constexpr int kTilesPerBlock = 8;        // consecutive tiles per block: the next tile's loads are in flight while this one is written
+
+// One launch serves many planes: tile index g belongs to the task whose [first_block, first_block + tiles) range holds it.
 template <int kBytes>
 __global__ void __launch_bounds__(kThreads)
-sangnom_turn_planes(const TurnTask* __restrict__ tasks, int ntasks, int flip_rows, int flip_cols)
+sangnom_turn_planes(const SN_GRID_CONSTANT TurnBatch batch, int ntasks, int total_tiles, int flip_rows, int flip_cols)
 {
+    const TurnTask* const tasks = batch.t;
     constexpr int m = 4 / kBytes;               // samples per word = cell side
     constexpr int TS = 32 * m;                  // tile side in samples
     SN_DYNAMIC_SMEM(smem_raw);
     uint32_t* const sm = reinterpret_cast<uint32_t*>(smem_raw);       // [m][32][33]
-
-    // binary search of the task (block-uniform)
-    int lo = 0, hi = ntasks - 1;
-    const int b = (int)blockIdx.x;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (tasks[mid].first_block <= b) lo = mid; else hi = mid - 1;
-    }
-    const TurnTask t = tasks[lo];
-    const int tile = b - t.first_block;
-    const int x0 = (tile % t.tiles_x) * TS, y0 = (tile / t.tiles_x) * TS;      // tile origin in the source
-    const int W = t.width, H = t.height;
     const int tx = (int)threadIdx.x & 31, ty = (int)threadIdx.x >> 5;
-    const unsigned char* const src = static_cast<const unsigned char*>(t.src);
-    unsigned char* const dst = static_cast<unsigned char*>(t.dst);
 
-    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)t.src_pitch | (uintptr_t)t.dst_pitch) & 3) == 0 &&
-                         (!flip_cols || H % m == 0);
-    if (aligned && x0 + TS <= W && y0 + TS <= H) {
-        // ---- fast path: whole tile, word accesses ----
+    struct Tile { const unsigned char* src; unsigned char* dst; long long sp, dp; int x0, y0, W, H; bool fast;
+                  int task, tiles_x, band_row0, rows_in_band, col, row; bool aligned; };
+    auto finish = [&](Tile& q) {
+        q.x0 = q.col * TS; q.y0 = (q.band_row0 + q.row) * TS;          // tile origin in the source
+        q.fast = q.aligned && q.x0 + TS <= q.W && q.y0 + TS <= q.H;
+    };
+    // Tile order: bands of kBandRows tile rows, inside a band down the columns first. The few hundred blocks that
+    // run at the same time then cover a patch that is many tiles wide AND high, so both the reads (contiguous
+    // along source rows) and the writes (contiguous along source columns) reach DRAM as runs of a few KB instead
+    // of isolated 128-byte pieces.
+    auto locate = [&](int g) -> Tile {
+        int lo = 0, hi = ntasks - 1;                                    // binary search of the task (block-uniform)
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (tasks[mid].first_block <= g) lo = mid; else hi = mid - 1;
+        }
+        const TurnTask& t = tasks[lo];
+        Tile q;
+        const int tile = g - t.first_block;
+        q.task = lo; q.tiles_x = t.tiles_x;
+        q.src = static_cast<const unsigned char*>(t.src); q.dst = static_cast<unsigned char*>(t.dst);
+        q.sp = t.src_pitch; q.dp = t.dst_pitch; q.W = t.width; q.H = t.height;
+        const int tiles_y = (t.height + TS - 1) / TS;
+        const int band = tile / (t.tiles_x * kBandRows), rem = tile - band * (t.tiles_x * kBandRows);
+        q.band_row0 = band * kBandRows;
+        q.rows_in_band = min(kBandRows, tiles_y - q.band_row0);
+        q.col = rem / q.rows_in_band; q.row = rem - q.col * q.rows_in_band;
+        q.aligned = ((reinterpret_cast<uintptr_t>(q.src) | reinterpret_cast<uintptr_t>(q.dst) | (uintptr_t)q.sp | (uintptr_t)q.dp) & 3) == 0 &&
+                    (!flip_cols || q.H % m == 0);
+        finish(q);
+        return q;
+    };
+    // the tile after q in the same order: one step down the column, or the top of the next column; crossing into
+    // another band or plane takes the full lookup
+    auto next_tile = [&](const Tile& q, int g) -> Tile {
+        Tile r = q;
+        if (++r.row == r.rows_in_band) { r.row = 0; if (++r.col == r.tiles_x) return locate(g); }
+        finish(r);
+        return r;
+    };
+    // the 4 cells (m words each) this thread moves of a whole tile
+    auto load_cells = [&](const Tile& q, uint32_t (&r)[4][m]) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int ci = ty + 8 * i;                                  // cell row inside the tile
-            uint32_t in[m], out[m];
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int k = 0; k < m; ++k)
-                in[k] = *reinterpret_cast<const uint32_t*>(src + (long long)(y0 + ci * m + k) * t.src_pitch + (long long)(x0 + tx * m) * kBytes);
-            cell_transpose<kBytes>(in, out);
+                r[i][k] = __ldg(reinterpret_cast<const uint32_t*>(q.src + (long long)(q.y0 + (ty + 8 * i) * m + k) * q.sp + (long long)(q.x0 + tx * m) * kBytes));
+    };
+
+    const int g0 = (int)blockIdx.x * kTilesPerBlock, g1 = min(g0 + kTilesPerBlock, total_tiles);
+    Tile cur = locate(g0);
+    uint32_t regs[4][m];
+    if (cur.fast) load_cells(cur, regs);
+    for (int g = g0; g < g1; ++g) {
+        Tile nxt = cur;
+        uint32_t ahead[4][m];
+        const bool more = g + 1 < g1;
+        if (more) { nxt = next_tile(cur, g + 1); if (nxt.fast) load_cells(nxt, ahead); }
+        if (cur.fast) {
+            // ---- whole tile, word accesses ----
 #pragma unroll
-            for (int j = 0; j < m; ++j) sm[(j * 32 + tx) * 33 + ci] = out[j];      // [j][cell col][cell row]
-        }
-        __syncthreads();
+            for (int i = 0; i < 4; ++i) {
+                uint32_t out[m];
+                cell_transpose<kBytes>(regs[i], out);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int oi = ty + 8 * i;                                  // source cell column = output cell row
+                for (int j = 0; j < m; ++j) sm[(j * 32 + tx) * 33 + ty + 8 * i] = out[j];      // [j][cell col][cell row]
+            }
+            __syncthreads();
 #pragma unroll
-            for (int j = 0; j < m; ++j) {
-                uint32_t w = sm[(j * 32 + oi) * 33 + tx];               // samples (x, y .. y+m-1), x = x0 + oi*m + j, y = y0 + tx*m
-                const int x = x0 + oi * m + j, y = y0 + tx * m;
-                const int orow = flip_rows ? W - 1 - x : x;
-                int ocol = y;
-                if (flip_cols) { ocol = H - y - m; w = reverse_samples<kBytes>(w); }
-                *reinterpret_cast<uint32_t*>(dst + (long long)orow * t.dst_pitch + (long long)ocol * kBytes) = w;
+            for (int i = 0; i < 4; ++i) {
+                const int oi = ty + 8 * i;                              // source cell column = output cell row
+#pragma unroll
+                for (int j = 0; j < m; ++j) {
+                    uint32_t w = sm[(j * 32 + oi) * 33 + tx];           // samples (x, y .. y+m-1), x = x0 + oi*m + j, y = y0 + tx*m
+                    const int x = cur.x0 + oi * m + j, y = cur.y0 + tx * m;
+                    const int orow = flip_rows ? cur.W - 1 - x : x;
+                    int ocol = y;
+                    if (flip_cols) { ocol = cur.H - y - m; w = reverse_samples<kBytes>(w); }
+                    *reinterpret_cast<uint32_t*>(cur.dst + (long long)orow * cur.dp + (long long)ocol * kBytes) = w;
+                }
+            }
+            __syncthreads();
+        } else {
+            // ---- edge tiles / unaligned planes: sample by sample ----
+            for (int e = (int)threadIdx.x; e < TS * TS; e += kThreads) {
+                const int x = cur.x0 + e % TS, y = cur.y0 + e / TS;     // consecutive threads: consecutive source columns
+                if (x >= cur.W || y >= cur.H) continue;
+                const int orow = flip_rows ? cur.W - 1 - x : x, ocol = flip_cols ? cur.H - 1 - y : y;
+                const unsigned char* sp = cur.src + (long long)y * cur.sp + (long long)x * kBytes;
+                unsigned char* dp = cur.dst + (long long)orow * cur.dp + (long long)ocol * kBytes;
+                if constexpr (kBytes == 1) *dp = *sp;
+                else if constexpr (kBytes == 2) *reinterpret_cast<uint16_t*>(dp) = *reinterpret_cast<const uint16_t*>(sp);
+                else *reinterpret_cast<uint32_t*>(dp) = *reinterpret_cast<const uint32_t*>(sp);
             }
         }
-        return;
-    }
-    // ---- edge tiles / unaligned planes: sample by sample ----
-    for (int e = (int)threadIdx.x; e < TS * TS; e += kThreads) {
-        const int ly = e / TS, lxx = e % TS;                            // consecutive threads: consecutive source columns
-        const int x = x0 + lxx, y = y0 + ly;
-        if (x >= W || y >= H) continue;
-        const int orow = flip_rows ? W - 1 - x : x, ocol = flip_cols ? H - 1 - y : y;
-        const unsigned char* s = src + (long long)y * t.src_pitch + (long long)x * kBytes;
-        unsigned char* d = dst + (long long)orow * t.dst_pitch + (long long)ocol * kBytes;
-        if constexpr (kBytes == 1) *d = *s;
-        else if constexpr (kBytes == 2) *reinterpret_cast<uint16_t*>(d) = *reinterpret_cast<const uint16_t*>(s);
-        else *reinterpret_cast<uint32_t*>(d) = *reinterpret_cast<const uint32_t*>(s);
+        if (more) {
+            cur = nxt;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < m; ++k) regs[i][k] = ahead[i][k];
+        }
     }
 }
 

@@ -210,7 +210,7 @@ SN_API int sangnom_cuda_chain_get_stats(sn_chain* chain, sn_chain_stats* out);
 SN_API const char* sangnom_cuda_chain_last_error(sn_chain* chain);
 
 /* The turn on its own, device planes: dst (height x width samples) = src (width x height) transposed (kind 0),
- * turned clockwise (1) or counter-clockwise (2). Synchronous with respect to `cuda_stream`. */
+ * turned clockwise (1) or counter-clockwise (2). Asynchronous on `cuda_stream` (a cudaStream_t as void*). */
 typedef struct sn_turn_plane {
     const void* src; ptrdiff_t src_pitch;
     void* dst; ptrdiff_t dst_pitch;

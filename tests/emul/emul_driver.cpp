@@ -70,17 +70,19 @@ int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long lo
 int emul_turn(int sample_bytes, int kind, const void* src, long long src_pitch, void* dst, long long dst_pitch, int width, int height)
 {
     const int TS = sn::turn::tile_side(sample_bytes);
-    sn::turn::TurnTask t{};
+    sn::turn::TurnBatch batch{};
+    sn::turn::TurnTask& t = batch.t[0];
     t.src = src; t.dst = dst; t.src_pitch = src_pitch; t.dst_pitch = dst_pitch; t.width = width; t.height = height;
     t.tiles_x = (width + TS - 1) / TS;
     t.first_block = 0;
-    const int blocks = t.tiles_x * ((height + TS - 1) / TS);
+    const int tiles = t.tiles_x * ((height + TS - 1) / TS);
+    const int blocks = (tiles + sn::turn::kTilesPerBlock - 1) / sn::turn::kTilesPerBlock;
     const int fr = kind == 2, fc = kind == 1;
     for (int b = 0; b < blocks; ++b) {
         auto body = [&] {
-            if (sample_bytes == 1) sn::turn::sangnom_turn_planes<1>(&t, 1, fr, fc);
-            else if (sample_bytes == 2) sn::turn::sangnom_turn_planes<2>(&t, 1, fr, fc);
-            else sn::turn::sangnom_turn_planes<4>(&t, 1, fr, fc);
+            if (sample_bytes == 1) sn::turn::sangnom_turn_planes<1>(batch, 1, tiles, fr, fc);
+            else if (sample_bytes == 2) sn::turn::sangnom_turn_planes<2>(batch, 1, tiles, fr, fc);
+            else sn::turn::sangnom_turn_planes<4>(batch, 1, tiles, fr, fc);
         };
         emul::run_block((unsigned)b, sn::turn::kThreads, sn::turn::smem_bytes(sample_bytes), body);
     }

@@ -67,6 +67,7 @@ def test_turn_planes_device(cuda, dtype, kind):
                                               for a, s, d in zip(srcs, d_src, d_dst)])
     torch.cuda.synchronize()
     assert lib.sangnom_cuda_turn_planes_device(srcs[0].itemsize, kind, planes, len(srcs), C.c_void_p(0)) == 0
+    torch.cuda.synchronize()
     for a, d in zip(srcs, d_dst):
         got = d.cpu().numpy().view(dtype)
         assert np.array_equal(got, [a.T, np.rot90(a, -1), np.rot90(a, 1)][kind])
