@@ -125,6 +125,7 @@ struct sn_ctx {
     DevBuf dev_state;
     // persistent-pool mode (SN_FLAG_PERSISTENT_POOL): the pool state between frames, ping-pong
     bool persistent = false;
+    bool saturate = false;               // SN_FLAG_SATURATE: the reference's SSE2 (opt=1) arithmetic flavour
     DevBuf carry[2];
     int carry_pos = 0;                   // carry[carry_pos] holds the state the next frame starts from
     DevBuf dev_tasks[kTaskRing];
@@ -324,7 +325,7 @@ int launch_passes(sn_ctx* ctx, const std::vector<std::vector<sn::PlaneTask>>& by
     size_t pos = 0;
     for (auto& v : by_pass) {
         if (v.empty()) continue;
-        SN_CUDA(ctx, sn::launch_plane_tasks(ctx->sample_bytes, dev_tasks + pos, (int)v.size(), sn::make_geometry(ctx->S, ctx->Hb), stream));
+        SN_CUDA(ctx, sn::launch_plane_tasks(ctx->sample_bytes, dev_tasks + pos, (int)v.size(), sn::make_geometry(ctx->S, ctx->Hb, ctx->saturate), stream));
         ctx->stats.kernel_launches += 1;
         ctx->stats.planes_processed += v.size();
         pos += v.size();
@@ -500,6 +501,7 @@ int sangnom_cuda_create(const sn_config* cfg, sn_ctx** out)
     for (int i = 0; i < kTaskRing; ++i)
         if ((e = cudaEventCreateWithFlags(&ctx->dev_task_free[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&ctx->trace_base)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    ctx->saturate = (cfg->flags & SN_FLAG_SATURATE) != 0;
     if (cfg->flags & SN_FLAG_PERSISTENT_POOL) {
         ctx->persistent = true;
         const size_t bytes = sn::plan_carry_bytes(S, Hb, cfg->sample_type);

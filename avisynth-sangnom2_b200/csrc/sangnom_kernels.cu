@@ -65,6 +65,18 @@ int cluster_split(int S, int seg_max)
     return G;
 }
 
+// One instantiation per (split over a cluster?, arithmetic flavour); shared-memory opt-in remembered per device.
+template <bool kClustered, bool kSat>
+cudaError_t launch_u8_variant(const PlaneTask* tasks, int ntasks, LaunchGeometry g, int G, int seg, cudaStream_t stream)
+{
+    static size_t configured[64] = {};
+    auto kernel = u8k::sangnom_u8_row_sweep<256, 2, kClustered, kSat>;
+    const size_t smem = u8k::smem_bytes(seg);
+    cudaError_t e = ensure_smem(kernel, smem, configured);
+    if (e != cudaSuccess) return e;
+    return launch_clustered(kernel, ntasks * G, seg / u8k::kCols, smem, G, stream, tasks, g, seg);
+}
+
 // 8-bit: 8 columns per thread, at most 2048 columns per block.
 cudaError_t launch_u8(const PlaneTask* tasks, int ntasks, LaunchGeometry g, cudaStream_t stream)
 {
@@ -72,21 +84,23 @@ cudaError_t launch_u8(const PlaneTask* tasks, int ntasks, LaunchGeometry g, cuda
     const int G = cluster_split(g.S, seg_max);
     const int seg = g.S / G;
     if (seg > 2048 || seg % u8k::kCols != 0) return cudaErrorInvalidValue;
-    const size_t smem = u8k::smem_bytes(seg);
-    static size_t configured[2][64] = {};
-    if (G == 1) {
-        auto kernel = u8k::sangnom_u8_row_sweep<256, 2, false>;
-        cudaError_t e = ensure_smem(kernel, smem, configured[0]);
-        if (e != cudaSuccess) return e;
-        return launch_clustered(kernel, ntasks, seg / u8k::kCols, smem, 1, stream, tasks, g, seg);
-    }
-    auto kernel = u8k::sangnom_u8_row_sweep<256, 2, true>;
-    cudaError_t e = ensure_smem(kernel, smem, configured[1]);
-    if (e != cudaSuccess) return e;
-    return launch_clustered(kernel, ntasks * G, seg / u8k::kCols, smem, G, stream, tasks, g, seg);
+    if (G == 1) return g.saturate ? launch_u8_variant<false, true>(tasks, ntasks, g, G, seg, stream) : launch_u8_variant<false, false>(tasks, ntasks, g, G, seg, stream);
+    return g.saturate ? launch_u8_variant<true, true>(tasks, ntasks, g, G, seg, stream) : launch_u8_variant<true, false>(tasks, ntasks, g, G, seg, stream);
 }
 
-// 16-bit / fp32: 4 columns per thread, at most 1024 columns per block.
+template <typename T, bool kClustered, bool kSat>
+cudaError_t launch_wide_variant(const PlaneTask* tasks, int ntasks, LaunchGeometry g, int G, int seg, cudaStream_t stream)
+{
+    static size_t configured[64] = {};
+    auto kernel = wide::sangnom_wide_row_sweep<T, 256, 2, kClustered, kSat>;
+    const size_t smem = wide::smem_bytes<T>(seg);
+    cudaError_t e = ensure_smem(kernel, smem, configured);
+    if (e != cudaSuccess) return e;
+    return launch_clustered(kernel, ntasks * G, seg / wide::kCols, smem, G, stream, tasks, g, seg);
+}
+
+// 16-bit / fp32: 4 columns per thread, at most 1024 columns per block. fp32 has one flavour (the SSE2 path computes the
+// same floats).
 template <typename T>
 cudaError_t launch_wide(const PlaneTask* tasks, int ntasks, LaunchGeometry g, cudaStream_t stream)
 {
@@ -94,18 +108,12 @@ cudaError_t launch_wide(const PlaneTask* tasks, int ntasks, LaunchGeometry g, cu
     const int G = cluster_split(g.S, seg_max);
     const int seg = g.S / G;
     if (seg > 1024 || seg % wide::kCols != 0) return cudaErrorInvalidValue;
-    const size_t smem = wide::smem_bytes<T>(seg);
-    static size_t configured[2][64] = {};
-    if (G == 1) {
-        auto kernel = wide::sangnom_wide_row_sweep<T, 256, 2, false>;
-        cudaError_t e = ensure_smem(kernel, smem, configured[0]);
-        if (e != cudaSuccess) return e;
-        return launch_clustered(kernel, ntasks, seg / wide::kCols, smem, 1, stream, tasks, g, seg);
+    constexpr bool kInt = !Flavour<T>::kFloat;
+    if constexpr (kInt) {
+        if (g.saturate)
+            return G == 1 ? launch_wide_variant<T, false, true>(tasks, ntasks, g, G, seg, stream) : launch_wide_variant<T, true, true>(tasks, ntasks, g, G, seg, stream);
     }
-    auto kernel = wide::sangnom_wide_row_sweep<T, 256, 2, true>;
-    cudaError_t e = ensure_smem(kernel, smem, configured[1]);
-    if (e != cudaSuccess) return e;
-    return launch_clustered(kernel, ntasks * G, seg / wide::kCols, smem, G, stream, tasks, g, seg);
+    return G == 1 ? launch_wide_variant<T, false, false>(tasks, ntasks, g, G, seg, stream) : launch_wide_variant<T, true, false>(tasks, ntasks, g, G, seg, stream);
 }
 
 }  // namespace

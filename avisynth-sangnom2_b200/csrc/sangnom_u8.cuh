@@ -98,6 +98,9 @@ struct Taps {
 // (f1, b1) = (f, b), as the lower row (f2, b2) = (b, f) (reference :103-106).
 struct Tap3 { uint32_t f[2], b[2]; };
 
+// kSat: the arithmetic of the reference's SSE2 path (SangNom2_SSE2.cpp:449-481) - 16-bit unsigned lanes, logical
+// shift, pack with saturation: a negative sum becomes 255, a quotient above 255 clamps.
+template <bool kSat>
 __device__ __forceinline__ void tap3_row(const Taps& t, Tap3& o)
 {
 #pragma unroll
@@ -112,6 +115,18 @@ __device__ __forceinline__ void tap3_row(const Taps& t, Tap3& o)
             const uint32_t u = c2 * 5u + 0x08000800u;
             fl[q] = ((m2 << 2) + u - p2) >> 3;
             bl[q] = ((p2 << 2) + u - m2) >> 3;
+            if constexpr (kSat) {
+                // lane value = (sum >> 3) + 256 in [224, 542]; w = value - 224: w < 32 <=> sum < 0 -> 255,
+                // else min(w - 32, 255)
+                auto sat = [](uint32_t v) {
+                    const uint32_t w = (v & 0x03FF03FFu) - 0x00E000E0u;
+                    const uint32_t z = __vminu2(__vmaxu2(w, 0x00200020u) - 0x00200020u, 0x00FF00FFu);
+                    const uint32_t neg = (((0x00200020u - __vminu2(w, 0x00200020u)) + 0x00FF00FFu) >> 8) & 0x00010001u;
+                    return z | (neg * 0xFFu);
+                };
+                fl[q] = sat(fl[q]);
+                bl[q] = sat(bl[q]);
+            }
         }
         o.f[h] = pack4(fl[0], fl[1]);
         o.b[h] = pack4(bl[0], bl[1]);
@@ -220,7 +235,7 @@ inline size_t smem_bytes(int seg_cols)
            kRing * sizeof(stage::Mbar) + ((sizeof(PlaneTask) + 15) & ~(size_t)15);
 }
 
-template <int kMaxThreads, int kMinBlocks, bool kClustered>
+template <int kMaxThreads, int kMinBlocks, bool kClustered, bool kSat = false>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
 sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int seg_cols)
 {
@@ -359,7 +374,7 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
             await_row(0);
             window(0, wa);
             Ta.build(wa);
-            tap3_row(Ta, ta);
+            tap3_row<kSat>(Ta, ta);
             t3_put(0, ta);
             // border row without a neighbour pair (reference GetFrame :380-391) and, for a one-pair-less plane, the kept row
             if (t.offset != 0) store8(0, make_uint2(wa[1], wa[2]));
@@ -370,7 +385,7 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
                 await_row(1);
                 window(1, wb);
                 Tb.build(wb);
-                tap3_row(Tb, tb);
+                tap3_row<kSat>(Tb, tb);
                 t3_put(1, tb);
                 if (npix == kCols) pair_costs(Ta, ta, Tb, tb, Pb); else straddle_costs(Ta, ta, Tb, tb, Pb);
             }
@@ -421,7 +436,7 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
                 await_row(r + 1);
                 window(r + 1, wc);
                 Tc.build(wc);
-                tap3_row(Tc, tc);
+                tap3_row<kSat>(Tc, tc);
                 t3_put(r + 1, tc);
                 if (kFull) pair_costs(Tb, tb, Tc, tc, Pb); else straddle_costs(Tb, tb, Tc, tc, Pb);
             }
@@ -476,11 +491,16 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
             // H7_k = Z_k + (X_k.hi, X_{k+1}.lo)  -> lanes (sum l[2k-3..2k+3], sum l[2k-2..2k+4])
             const uint32_t Z0 = Wm1 + W0 + W1, Z1 = W0 + W1 + W2, Z2 = W1 + W2 + W3, Z3 = W2 + W3 + W4, Z4 = W3 + W4 + W5;
             const uint32_t X0 = Z0 + Wm2, X1 = Z1 + Wm1, X2 = Z2 + W0, X3 = Z3 + W1, X4 = Z4 + W2;
+            // (B << 4) | rank in both lanes, B = the blurred cost narrowed to 8 bits: wrapped (:152), or clamped for the SSE2 flavour
+            auto narrow_key = [&](uint32_t sum) -> uint32_t {
+                if constexpr (kSat) return __vminu2(sum & 0xFFF0FFF0u, 0x0FF00FF0u) | rank2(i);
+                else return (sum & keymask) | rank2(i);
+            };
             uint32_t key[4];
-            key[0] = ((Z0 + __funnelshift_r(X0, X1, 16)) & keymask) | rank2(i);
-            key[1] = ((Z1 + __funnelshift_r(X1, X2, 16)) & keymask) | rank2(i);
-            key[2] = ((Z2 + __funnelshift_r(X2, X3, 16)) & keymask) | rank2(i);
-            key[3] = ((Z3 + __funnelshift_r(X3, X4, 16)) & keymask) | rank2(i);
+            key[0] = narrow_key(Z0 + __funnelshift_r(X0, X1, 16));
+            key[1] = narrow_key(Z1 + __funnelshift_r(X1, X2, 16));
+            key[2] = narrow_key(Z2 + __funnelshift_r(X2, X3, 16));
+            key[3] = narrow_key(Z3 + __funnelshift_r(X3, X4, 16));
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 M[i][q] += key[q] >> 4;                                     // LEA.HI: P[r+1] + B[r] + leak(i)

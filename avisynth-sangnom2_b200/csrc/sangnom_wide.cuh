@@ -76,7 +76,7 @@ __device__ __forceinline__ void load_window(const T* __restrict__ row, int x0, i
     for (int e = kHalo + 1; e < kWin; ++e) if (e > last) w[e] = w[e - 1];
 }
 
-template <typename T, int kMaxThreads, int kMinBlocks, bool kClustered>
+template <typename T, int kMaxThreads, int kMinBlocks, bool kClustered, bool kSat = false>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
 sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int seg_cols)
 {
@@ -160,7 +160,7 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
 #pragma unroll
             for (int c = 0; c < kCols; ++c) {
                 I cost[kNumCost];
-                raw_costs<T, I, kWin, kHalo>(wc, wn, c, cost);
+                raw_costs<T, I, kWin, kHalo, kSat>(wc, wn, c, cost);
                 if (c < npix) {
 #pragma unroll
                     for (int i = 0; i < kNumCost; ++i) P[i][c] = cost[i];
@@ -259,7 +259,9 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
 #pragma unroll
                 for (int c = 0; c < kCols; ++c) {
                     if (c > 0) s += Lw[c + 7] - Lw[c];
-                    const int key = (int)(((unsigned)s & ((unsigned)Flavour<T>::kMask << 4)) | (unsigned)k);   // wrapT(s / 16) << 4 | rank
+                    // narrowT(s / 16) << 4 | rank: wrapped (:152), or clamped for the SSE2 flavour (SangNom2_SSE2.cpp:807)
+                    const unsigned kept = kSat ? min((unsigned)s, ((unsigned)Flavour<T>::kMask << 4) | 15u) & ~15u : (unsigned)s & ((unsigned)Flavour<T>::kMask << 4);
+                    const int key = (int)(kept | (unsigned)k);
                     B4[c] = key >> 4;
                     kmin[c] = min(kmin[c], key);
                 }
@@ -277,7 +279,7 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
                 int rank;
                 if constexpr (Flavour<T>::kFloat) rank = fmin[c] > t.thr_f ? 0 : frank[c];
                 else rank = kmin[c] & 15;
-                px[c] = interpolate_rank<T, I, kWin, kHalo>(wa, wb, c, rank);
+                px[c] = interpolate_rank<T, I, kWin, kHalo, kSat>(wa, wb, c, rank);
             }
             store_px(plane + (long long)(t.offset + 2 * (r - 1) + 1) * pitch, px);
             if (t.copy_kept) {

@@ -32,7 +32,9 @@ SangNom2::SangNom2(PClip _child, int order, int aa, int aac, int threads, bool d
     : GenericVideoFilter(_child), order_(order), dh_(dh), aaf_{ 0.0f, 0.0f, 0.0f }, process_plane_{ luma, chroma, chroma }
 {
     (void)threads;   // dummy parameter, as in the reference (README.md:40-41)
-    (void)opt;       // validated by the factory; selects nothing here - there is one code path
+    // opt is validated by the factory. There is one code path; opt=1 selects the ARITHMETIC of the reference's SSE2
+    // path (narrowing saturates, SangNom2_SSE2.cpp:449-517,761,807) for users who compare against an SSE2 build of the
+    // reference; opt=0 and opt=-1 give the opt=0 C++ arithmetic (narrowing wraps), the parity contract.
     has_at_least_v8_ = env->FunctionExists("propShow");
     sample_bytes_ = vi.ComponentSize();
     plane_count_ = vi.NumComponents() < 3 ? vi.NumComponents() : 3;
@@ -56,6 +58,7 @@ SangNom2::SangNom2(PClip _child, int order, int aa, int aac, int threads, bool d
     // instance (bit-compatible with a sequential single-instance reference run where that is not frame-pure:
     // widths that are not a multiple of 32, luma=false with subsampled chroma). Frames then run one after another.
     if (env_int("SANGNOM_B200_PERSISTENT", 0, 0, 1)) cfg.flags |= SN_FLAG_PERSISTENT_POOL;
+    if (opt == 1) cfg.flags |= SN_FLAG_SATURATE;
     if (sangnom_cuda_create(&cfg, &ctx_) != SN_OK)
         env->ThrowError("SangNom2: %s", sangnom_cuda_last_error(nullptr));
 }

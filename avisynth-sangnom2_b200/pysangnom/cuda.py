@@ -18,6 +18,7 @@ SN_OK, SN_ERR_INVALID, SN_ERR_CUDA, SN_ERR_UNSUPPORTED, SN_ERR_NOMEM = range(5)
 MODE_COPY, MODE_FIELD, MODE_DH, MODE_INPLACE = range(4)
 ABI_VERSION = 1
 FLAG_PERSISTENT_POOL = 1
+FLAG_SATURATE = 2
 
 EXPORTS = [
     "sangnom_cuda_abi_version", "sangnom_cuda_create", "sangnom_cuda_destroy", "sangnom_cuda_process_planes",

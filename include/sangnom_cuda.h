@@ -79,6 +79,11 @@ enum sn_mode {
  * dependent, so this mode runs one plane pass at a time: use it for bit-compatibility with a sequential reference
  * run, not for throughput. Default (0): every frame starts from a zero-filled pool (a fresh instance per frame). */
 #define SN_FLAG_PERSISTENT_POOL 1
+/* Arithmetic flavour of the reference's SSE2 path (opt=1, and what opt=-1 picks on an SSE2 CPU; SangNom2_SSE2.cpp):
+ * the same three stages, but the 3-tap value and the blurred cost are narrowed with SATURATION (:449-517, :761, :807)
+ * where the opt=0 C++ path wraps (SangNom2.cpp:63-64, :152). Integer formats only; fp32 is identical in both. Default
+ * (0): opt=0 arithmetic, the parity contract. */
+#define SN_FLAG_SATURATE 2
 
 typedef struct sn_config {
     int abi_version;         /* SANGNOM_CUDA_ABI_VERSION */

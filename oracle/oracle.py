@@ -48,6 +48,8 @@ def _load():
                                       C.POINTER(C.c_ssize_t), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float),
                                       C.c_void_p]
+        L.sn_oracle_set_saturating.restype = None
+        L.sn_oracle_set_saturating.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -77,14 +79,16 @@ def resolve_offset(order, parity):
     return 0 if order == 1 else 1
 
 
-def oracle_frame(planes, bits, order=1, aa=48, aac=0, dh=False, luma=True, chroma=True, parity=True, pool=None):
+def oracle_frame(planes, bits, order=1, aa=48, aac=0, dh=False, luma=True, chroma=True, parity=True, pool=None, saturate=False):
     """Run one frame through the C restatement. `planes`: list of 1..4 2-D numpy arrays (Y[,U,V[,A]]).
 
     Returns the output planes (alpha, if present, is returned as a copy of the source scaled to the
     output height by row duplication for dh - the reference leaves it unwritten).
     pool=None => fresh zero-filled pool (the parity contract); pass new_pool(...) to chain frames.
+    saturate=True => the arithmetic of the reference's opt=1 (SSE2) path instead of opt=0.
     """
     L = _load()
+    L.sn_oracle_set_saturating(int(bool(saturate)))
     n = min(len(planes), 3)
     dt = planes[0].dtype
     sb = dt.itemsize
@@ -101,6 +105,7 @@ def oracle_frame(planes, bits, order=1, aa=48, aac=0, dh=False, luma=True, chrom
                            (C.c_int * n)(*[p.shape[1] for p in srcs]), (C.c_int * n)(*[p.shape[0] for p in srcs]),
                            n, sb, wy, out_h, int(dh), off, (C.c_int * n)(*[int(b) for b in proc]),
                            (C.c_float * n)(*thr), pool.ctypes.data if pool is not None else None)
+    L.sn_oracle_set_saturating(0)
     if rc != 0:
         raise RuntimeError(f"oracle failed rc={rc}")
     if len(planes) == 4:

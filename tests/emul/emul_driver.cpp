@@ -17,7 +17,7 @@ extern "C" {
 int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long long* pitch_bytes, const void* const* srcs,
                const long long* src_pitch_bytes, const int* widths,
                const int* heights, const int* offsets, const float* thresholds, int pool_width, int pool_height, int cluster,
-               void* carry_in, void* carry_out)
+               void* carry_in, void* carry_out, int saturate)
 {
     // carry_in/carry_out != NULL: persistent-pool mode, the pool state (plan_carry_bytes) before and after this frame
     const int S = (pool_width + 31) & ~31, Hb = (pool_height + 1) >> 1;
@@ -50,14 +50,18 @@ int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long lo
         t.thr_f = thresholds[q];
         t.thr_i = sample_bytes == 1 ? ((int)thresholds[q] & 0xFF) : ((int)thresholds[q] & 0xFFFF);
         t.in = geo[q].in; t.out = geo[q].out;
-        const sn::LaunchGeometry g = sn::make_geometry(S, Hb);
+        const sn::LaunchGeometry g = sn::make_geometry(S, Hb, saturate != 0);
         const unsigned G = (unsigned)cluster;
         const int cols = sample_bytes == 1 ? sn::u8k::kCols : sn::wide::kCols;
         if (S % (int)(G * cols) != 0) return -1;
         const int seg = S / (int)G;
         const unsigned threads = (unsigned)(seg / cols);
-        if (sample_bytes == 1)
+        if (sample_bytes == 1 && saturate)
+            emul::run_cluster(0, G, threads, sn::u8k::smem_bytes(seg), [&] { sn::u8k::sangnom_u8_row_sweep<1024, 1, true, true>(&t, g, seg); });
+        else if (sample_bytes == 1)
             emul::run_cluster(0, G, threads, sn::u8k::smem_bytes(seg), [&] { sn::u8k::sangnom_u8_row_sweep<1024, 1, true>(&t, g, seg); });
+        else if (sample_bytes == 2 && saturate)
+            emul::run_cluster(0, G, threads, sn::wide::smem_bytes<uint16_t>(seg), [&] { sn::wide::sangnom_wide_row_sweep<uint16_t, 1024, 1, true, true>(&t, g, seg); });
         else if (sample_bytes == 2)
             emul::run_cluster(0, G, threads, sn::wide::smem_bytes<uint16_t>(seg), [&] { sn::wide::sangnom_wide_row_sweep<uint16_t, 1024, 1, true>(&t, g, seg); });
         else

@@ -147,3 +147,31 @@ def test_separated_fields_input(cuda):
         exp = O.oracle_frame(fr, fmt.bits, order=0, aa=48, aac=48, parity=parity_of(i))
         assert_planes_equal(got[i][:3], exp[:3], f"fields frame {i}")
     assert st["h2d_bytes"] * 2 <= st["d2h_bytes"] + 4 * 3 * 16 * 288      # staged rows are padded to 16 bytes
+
+
+SATURATING = [("yv12_720", "YV12", 720, 480, dict(order=1, aa=48, aac=48)), ("420p8_1080p", "YUV420P8", 1920, 1080, dict(order=0, aa=48, aac=48)),
+              ("444p16_dh", "YUV444P16", 200, 120, dict(dh=True, aa=48, aac=48)), ("420p10", "YUV420P10", 960, 540, dict(order=2, aa=48, aac=20)),
+              ("420ps", "YUV420PS", 320, 240, dict(order=2, aa=48, aac=24)), ("y8_4k_cluster", "Y8", 4096, 64, dict(order=1, aa=128))]
+
+
+@pytest.mark.parametrize("case", SATURATING, ids=[c[0] for c in SATURATING])
+def test_saturating_flavour(cuda, case):
+    """SN_FLAG_SATURATE: the arithmetic of the reference's SSE2 path (opt=1). Checker: the oracle's saturating flavour,
+    pinned to the compiled reference run with opt=1 in tests/test_oracle.py."""
+    from oracle import oracle as O
+    from pysangnom.clips import make_frame
+    from pysangnom.fakehost import FORMATS
+    name, fmtname, w, h, kw = case
+    fmt = FORMATS[fmtname]
+    frames = [make_frame(500 + len(name), w, h, fmt, "noise", i) for i in range(2)]
+    dh = kw.get("dh", False)
+    args = dict(order=kw.get("order", 1), aa=kw.get("aa", 48), aac=kw.get("aac", 0), dh=dh)
+    with cuda.Context(fmt.sample_bytes, w, h * 2 if dh else h, flags=cuda.FLAG_SATURATE) as ctx:
+        got = ctx.process_frames(frames, fmt.bits, parities=[parity_of(i) for i in range(2)], **args)
+    differs = False
+    for i, fr in enumerate(frames):
+        exp = O.oracle_frame(fr, fmt.bits, parity=parity_of(i), saturate=True, **args)
+        assert_planes_equal(got[i][:3], exp[:3], f"saturating {name} frame {i}")
+        wrap = O.oracle_frame(fr, fmt.bits, parity=parity_of(i), **args)
+        differs |= any(not np.array_equal(a, b) for a, b in zip(exp[:3], wrap[:3]))
+    assert differs or fmt.sample_bytes == 4 or fmt.bits == 10

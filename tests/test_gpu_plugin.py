@@ -88,6 +88,20 @@ def test_persistent_mode_equals_one_long_lived_reference_instance(monkeypatch, f
         assert_planes_equal(got[i][:3], ref[i][:3], f"persistent {fmtname} {kw} frame {i}")
 
 
+@pytest.mark.skipif(O.reference_plugin_path() is None, reason="oracle/_ref not built")
+@pytest.mark.parametrize("fmtname,w,h,kw", [("YV12", 352, 288, dict(order=0, aa=48, aac=48)), ("YUV420P16", 176, 144, dict(order=2, aa=48, aac=48)),
+                                            ("YUV444P10", 200, 120, dict(dh=True, aa=30)), ("YUV420PS", 176, 144, dict(order=1, aa=48, aac=24))])
+def test_opt1_selects_the_sse2_arithmetic(fmtname, w, h, kw):
+    """SangNom2(opt=1) on our plugin == the reference's SSE2 path (opt=1 on a host that reports SSE2)."""
+    from pysangnom.fakehost import CPUF_SSE2
+    fmt = FORMATS[fmtname]
+    frames = [make_frame(19, w, h, fmt, "noise", i) for i in range(3)]
+    ref = run_plugin(O.reference_plugin_path(), fmt, w, h, frames, dict(opt=1, **kw), fresh=True, cpu_flags=CPUF_SSE2)
+    got = run_plugin(OURS, fmt, w, h, frames, dict(opt=1, **kw), cpu_flags=CPUF_SSE2)
+    for i in range(len(frames)):
+        assert_planes_equal(got[i][:3], ref[i][:3], f"opt=1 {fmtname} {kw} frame {i}")
+
+
 def test_legacy_semantics_without_reference():
     """SangNom(order=0) keeps the bottom field, (order=2) is double-rate; aac takes the script's opt."""
     fmt = FORMATS["YV12"]

@@ -27,13 +27,13 @@ def emul():
     L.emul_frame.restype = C.c_int
     L.emul_frame.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.POINTER(C.c_void_p),
                              C.POINTER(C.c_longlong), C.POINTER(C.c_int),
-                             C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+                             C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     L.emul_carry_bytes.restype = C.c_size_t
     L.emul_carry_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     return L
 
 
-def emulate(L, planes, bits, order=1, aa=48, aac=0, dh=False, luma=True, chroma=True, parity=True, cluster=1, out_of_place=False, carry=None):
+def emulate(L, planes, bits, order=1, aa=48, aac=0, dh=False, luma=True, chroma=True, parity=True, cluster=1, out_of_place=False, carry=None, saturate=False):
     """Frame-level host logic in numpy (field placement, plane skipping), plane passes through the emulated kernel.
     out_of_place: the kept rows are handed to the kernel as a separate packed field buffer (what the host path
     uploads) and the kernel writes them into the dst plane itself.
@@ -67,7 +67,7 @@ def emulate(L, planes, bits, order=1, aa=48, aac=0, dh=False, luma=True, chroma=
                           (C.c_int * n)(*[outs[p].shape[0] for p in proc]), (C.c_int * n)(*[off] * n),
                           (C.c_float * n)(*[cuda.threshold(aa if p == 0 else aac, bits, sb) for p in proc]),
                           outs[0].shape[1], outs[0].shape[0], cluster,
-                          carry[0].ctypes.data if carry else None, carry[1].ctypes.data if carry else None)
+                          carry[0].ctypes.data if carry else None, carry[1].ctypes.data if carry else None, int(saturate))
         assert rc == 0
     return outs
 
@@ -162,3 +162,25 @@ def test_turn_kernel(emul, dtype, w, h, kind):
     assert emul.emul_turn(a.itemsize, kind, a.ctypes.data, a.strides[0], out.ctypes.data, out.strides[0], w, h) == 0
     exp = [a.T, np.rot90(a, -1), np.rot90(a, 1)][kind]
     assert np.array_equal(out, exp)
+
+
+SAT_CASES = [("Y8", 100, 30, dict(order=1, aa=48), "noise", 1), ("YV12", 96, 64, dict(order=0, aa=48, aac=48), "noise", 1), ("YV12", 256, 36, dict(order=2, aa=128, aac=128), "noise", 4),
+             ("YUV422P8", 68, 30, dict(order=2, aa=30, aac=90), "edges", 1), ("Y16", 40, 12, dict(order=1, aa=128), "noise", 1), ("YUV420P16", 96, 48, dict(order=0, aa=48, aac=48), "noise", 2),
+             ("YUV420P10", 100, 40, dict(order=1, aa=48, aac=20), "noise", 1), ("YUV444P16", 44, 20, dict(dh=True, aa=48, aac=48), "noise", 1), ("YUV420PS", 96, 48, dict(order=2, aa=48, aac=24), "noise", 1)]
+
+
+@pytest.mark.parametrize("fmtname,w,h,kw,kind,cluster", SAT_CASES, ids=[f"{c[0]}_{c[1]}x{c[2]}_{i}" for i, c in enumerate(SAT_CASES)])
+def test_saturating_flavour_matches_oracle(emul, fmtname, w, h, kw, kind, cluster):
+    """SN_FLAG_SATURATE kernels (the reference's SSE2 arithmetic) against the oracle's saturating flavour, which
+    tests/test_oracle.py pins to the compiled reference run with opt=1."""
+    fmt = FORMATS[fmtname]
+    differs = False
+    for i in range(2):
+        fr = make_frame(131, w, h, fmt, kind, i)
+        got = emulate(emul, fr, fmt.bits, parity=(i == 0), cluster=cluster, saturate=True, **kw)
+        exp = O.oracle_frame(fr, fmt.bits, parity=(i == 0), saturate=True, **kw)
+        assert_planes_equal(got, exp[:3], f"saturating {fmtname} {w}x{h} {kw} frame {i}")
+        wrap = O.oracle_frame(fr, fmt.bits, parity=(i == 0), **kw)
+        differs |= any(not np.array_equal(a, b) for a, b in zip(exp[:3], wrap[:3]))
+    if fmtname in ("Y8", "YV12") and kind == "noise":
+        assert differs, "case does not exercise the saturation"
