@@ -14,6 +14,8 @@
 #include "sangnom_arith.cuh"
 #include "sangnom_cluster.cuh"
 
+#include <type_traits>
+
 #ifndef SN_DYNAMIC_SMEM
 #define SN_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
@@ -142,12 +144,26 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
         return nullptr;
     };
 
-    // Raw cost row `row` of the pool into P: pixels where I have them and the pair exists (windows wc = K[row-1],
-    // wn = K[row]), else the handed-over state.
-    auto cost_row = [&](int row, const I (&wc)[kWin], const I (&wn)[kWin], I (&P)[kNumCost][kCols]) {
-        const bool pair = row <= n - 1;          // pool row j+1 holds the costs of the pair (K[j], K[j+1])
-        const bool pixels = pair && npix > 0;
-        if (!(pixels && npix == kCols)) {
+    // window of kept row j: interior threads of an aligned plane take three vector loads, nothing else
+    const bool interior = vec && x0 >= kHalo && x0 + kCols + kHalo <= W;
+    auto window = [&](int j, I (&w)[kWin]) {
+        const T* row = kept_row(j);
+        if (interior) {
+            I v[4];
+            load4(row + x0 - 4, v); w[0] = v[0]; w[1] = v[1]; w[2] = v[2]; w[3] = v[3];
+            load4(row + x0, v); w[4] = v[0]; w[5] = v[1]; w[6] = v[2]; w[7] = v[3];
+            load4(row + x0 + 4, v); w[8] = v[0]; w[9] = v[1]; w[10] = v[2]; w[11] = v[3];
+        } else {
+            load_window<T, I>(row, x0, W, vec, w);
+        }
+    };
+
+    // Raw cost row `row` of the pool into P (windows wc = K[row-1], wn = K[row]).
+    // kFull: all my columns carry pixels. kPair: the pair (K[row-1], K[row]) exists. Where there are no pixel costs
+    // the handed-over state of the previous pass (or the pool's zero) stands in.
+    auto cost_row = [&](auto full, auto pairrow, int row, const I (&wc)[kWin], const I (&wn)[kWin], I (&P)[kNumCost][kCols]) {
+        constexpr bool kFull = decltype(full)::value, kPair = decltype(pairrow)::value;
+        if constexpr (!(kFull && kPair)) {
             size_t stride;
             const T* st = state_row(t.in, row, stride);
 #pragma unroll
@@ -156,14 +172,16 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
                 else { P[i][0] = P[i][1] = P[i][2] = P[i][3] = I(0); }
             }
         }
-        if (pixels) {
+        if constexpr (kPair) {
+            if (kFull || npix > 0) {
 #pragma unroll
-            for (int c = 0; c < kCols; ++c) {
-                I cost[kNumCost];
-                raw_costs<T, I, kWin, kHalo, kSat>(wc, wn, c, cost);
-                if (c < npix) {
+                for (int c = 0; c < kCols; ++c) {
+                    I cost[kNumCost];
+                    raw_costs<T, I, kWin, kHalo, kSat>(wc, wn, c, cost);
+                    if (kFull || c < npix) {
 #pragma unroll
-                    for (int i = 0; i < kNumCost; ++i) P[i][c] = cost[i];
+                        for (int i = 0; i < kNumCost; ++i) P[i][c] = cost[i];
+                    }
                 }
             }
         }
@@ -176,10 +194,11 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
 #pragma unroll
     for (int e = 0; e < kWin; ++e) { wa[e] = I(0); wb[e] = I(0); wc[e] = I(0); }
     if (npix > 0) {
-        load_window<T, I>(kept_row(0), x0, W, vec, wb);
-        if (n > 1) load_window<T, I>(kept_row(1), x0, W, vec, wc);
+        window(0, wb);
+        if (n > 1) window(1, wc);
     }
-    cost_row(1, wb, wc, M);
+    if (n > 1) cost_row(std::false_type{}, std::true_type{}, 1, wb, wc, M);
+    else cost_row(std::false_type{}, std::false_type{}, 1, wb, wc, M);
     // after this the loop invariant holds at r = 1: wa = K[0], wb = K[1]
 #pragma unroll
     for (int e = 0; e < kWin; ++e) { wa[e] = wb[e]; wb[e] = wc[e]; }
@@ -187,33 +206,47 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
     const int tkey = (int)min((long long)t.thr_i + 1, 0x7FFFFFFLL) << 4;      // (thr+1) << 4: "every cost above the threshold"
     const bool exporting = t.out.a != nullptr || t.out.b != nullptr;
 
-    for (int r = 1; r <= R; ++r) {
+    // One pool row. kFull: every thread of the warp owns 4 pixel columns. kPair: pool row r+1 is a pair row
+    // (r + 1 <= n - 1). kExport: some thread of the warp hands this row's blurred costs to the next pass.
+    auto row_step = [&](auto full, auto pairrow, auto exportrow, int r) {
+        constexpr bool kFull = decltype(full)::value, kPair = decltype(pairrow)::value, kExport = decltype(exportrow)::value;
+        const bool pixels = kFull || npix > 0;
         // pull the kept row two iterations ahead towards L1 (no register cost)
-        if (r + 3 <= n - 1 && npix > 0) prefetch_l1(kept_row(r + 3) + x0);
+        if (kPair && pixels && r + 3 <= n - 1) prefetch_l1(kept_row(r + 3) + x0);
 
-        // ---- P[r+1]; L = M + P[r+1] into the shared row (and the neighbours' pads); M keeps P[r+1] ----
-        if (r + 1 <= n - 1 && npix > 0) load_window<T, I>(kept_row(r + 1), x0, W, vec, wc);
+        // ---- P[r+1]; L = M + P[r+1] into the shared row; M keeps P[r+1] ----
+        if (kPair && pixels) window(r + 1, wc);
         I* const Lrow = Lbase + (size_t)(r & 1) * kNumCost * LS + kHalo;
         {
             I P[kNumCost][kCols];
-            cost_row(r + 1, wb, wc, P);
+            cost_row(full, pairrow, r + 1, wb, wc, P);
 #pragma unroll
             for (int i = 0; i < kNumCost; ++i) {
-                I* row = Lrow + i * LS;
                 I L[4];
 #pragma unroll
                 for (int c = 0; c < kCols; ++c) { L[c] = add2(M[i][c], P[i][c]); M[i][c] = P[i][c]; }
+                I* row = Lrow + i * LS;
                 if constexpr (Flavour<T>::kFloat) *reinterpret_cast<float4*>(row + lx) = make_float4(L[0], L[1], L[2], L[3]);
                 else *reinterpret_cast<uint4*>(row + lx) = make_uint4((uint32_t)L[0], (uint32_t)L[1], (uint32_t)L[2], (uint32_t)L[3]);
+            }
+        }
+        // the segment's edge threads fill the 3-column pads: clamp at the pool's ends (:144-152 clamps at the pool
+        // stride), the neighbour block's shared row otherwise. Their own L values are re-read from the row just written.
+        if (seg_first | seg_last) {
+#pragma unroll
+            for (int i = 0; i < kNumCost; ++i) {
+                I* row = Lrow + i * LS;
                 if (seg_first) {
-                    if (plane_first) { row[-1] = L[0]; row[-2] = L[0]; row[-3] = L[0]; }                         // clamp at column 0
-                    else { cl::store_remote(row + seg_cols, crank - 1, L[0]); cl::store_remote(row + seg_cols + 1, crank - 1, L[1]);
-                           cl::store_remote(row + seg_cols + 2, crank - 1, L[2]); }
+                    const I l0 = row[lx], l1 = row[lx + 1], l2 = row[lx + 2];
+                    if (plane_first) { row[-1] = l0; row[-2] = l0; row[-3] = l0; }
+                    else { cl::store_remote(row + seg_cols, crank - 1, l0); cl::store_remote(row + seg_cols + 1, crank - 1, l1);
+                           cl::store_remote(row + seg_cols + 2, crank - 1, l2); }
                 }
                 if (seg_last) {
-                    if (plane_last) { row[seg_cols] = L[3]; row[seg_cols + 1] = L[3]; row[seg_cols + 2] = L[3]; } // clamp at column S-1
-                    else { cl::store_remote(row - 3, crank + 1, L[1]); cl::store_remote(row - 2, crank + 1, L[2]);
-                           cl::store_remote(row - 1, crank + 1, L[3]); }
+                    const I l1 = row[lx + 1], l2 = row[lx + 2], l3 = row[lx + 3];
+                    if (plane_last) { row[seg_cols] = l3; row[seg_cols + 1] = l3; row[seg_cols + 2] = l3; }
+                    else { cl::store_remote(row - 3, crank + 1, l1); cl::store_remote(row - 2, crank + 1, l2);
+                           cl::store_remote(row - 1, crank + 1, l3); }
                 }
             }
         }
@@ -221,7 +254,8 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
 
         // ---- B[r] per cost buffer, min key, M = B[r] + P[r+1], hand-over ----
         size_t out_stride = 0;
-        T* const out_ptr = exporting ? state_row(t.out, r, out_stride) : nullptr;
+        T* out_ptr = nullptr;
+        if constexpr (kExport) out_ptr = state_row(t.out, r, out_stride);
         int kmin[kCols];        // integer flavours: min over (cost << 4 | rank) keys, threshold folded in
         float fmin[kCols];      // fp32: running minimum and the rank that first reached it
         int frank[kCols];
@@ -268,11 +302,11 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
             }
 #pragma unroll
             for (int c = 0; c < kCols; ++c) M[i][c] = add2(B4[c], M[i][c]);
-            if (out_ptr != nullptr) store4(out_ptr + i * out_stride, B4);
+            if constexpr (kExport) { if (out_ptr != nullptr) store4(out_ptr + i * out_stride, B4); }
         }
 
         // ---- interpolate the picture row between K[r-1] and K[r] ----
-        if (r <= n - 1 && npix > 0) {
+        if ((kPair || r <= n - 1) && pixels) {
             I px[kCols];
 #pragma unroll
             for (int c = 0; c < kCols; ++c) {
@@ -281,15 +315,45 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
                 else rank = kmin[c] & 15;
                 px[c] = interpolate_rank<T, I, kWin, kHalo, kSat>(wa, wb, c, rank);
             }
-            store_px(plane + (long long)(t.offset + 2 * (r - 1) + 1) * pitch, px);
+            T* const orow = plane + (long long)(t.offset + 2 * (r - 1) + 1) * pitch;
+            if (kFull && vec_out) store4(orow + x0, px); else store_px(orow, px);
             if (t.copy_kept) {
                 const I keptrow[4] = { wa[4], wa[5], wa[6], wa[7] };
-                store_px(plane + (long long)(t.offset + 2 * (r - 1)) * pitch, keptrow);
+                if (kFull && vec_out) store4(orow - pitch + x0, keptrow); else store_px(orow - pitch, keptrow);
             }
         }
 #pragma unroll
         for (int e = 0; e < kWin; ++e) { wa[e] = wb[e]; wb[e] = wc[e]; }
-    }
+    };
+    // does any thread of my warp export pool row r? (warp-uniform, so the variants of a row keep warps whole)
+    auto export_row = [&](int r) -> bool {
+        if (!exporting) return false;
+        size_t stride;
+        const bool mine = state_row(t.out, r, stride) != nullptr;
+#ifdef SN_HOST_EMULATION
+        return mine;
+#else
+        return __any_sync(0xFFFFFFFFu, mine);
+#endif
+    };
+    auto sweep = [&](auto full) {
+        int r = 1;
+        for (; r <= n - 2 && r <= R; ++r) {                                  // rows whose lower neighbour row is a pair row
+            if (export_row(r)) row_step(full, std::true_type{}, std::true_type{}, r);
+            else row_step(full, std::true_type{}, std::false_type{}, r);
+        }
+        for (; r <= R; ++r) {                                               // the last picture row and rows swept for the next pass only
+            if (export_row(r)) row_step(full, std::false_type{}, std::true_type{}, r);
+            else row_step(full, std::false_type{}, std::false_type{}, r);
+        }
+    };
+    // warp-uniform choice, so that a warp never splits over the copies of the row barrier
+#ifdef SN_HOST_EMULATION
+    const bool warp_full = npix == kCols;
+#else
+    const bool warp_full = __all_sync(0xFFFFFFFFu, npix == kCols);
+#endif
+    if (warp_full) sweep(std::true_type{}); else sweep(std::false_type{});
 }
 
 template <typename T> inline size_t smem_bytes(int seg_cols) { return (size_t)2 * kNumCost * (seg_cols + 2 * kHalo) * sizeof(typename Flavour<T>::I); }
