@@ -9,6 +9,11 @@
 #include "sangnom_kernels.h"
 #include "sangnom_plan.h"
 
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <thread>
+
 #include <cuda.h>      // driver API types only; the entry point is looked up at run time (no libcuda link dependency)
 
 #include <algorithm>
@@ -26,6 +31,95 @@
 namespace {
 
 thread_local std::string g_create_error;
+
+// Host-side row copies (packing pageable frames into pinned staging, unpacking finished planes, whole-plane copies of
+// planes that are not interpolated - the reference's BitBlt/memcpy, SangNom2.cpp:361-377) are memory-bound and a single
+// thread moves only a few GB/s, far less than the PCIe link behind it. They are collected per chunk and run by a
+// small pool of worker threads; the calling thread takes part.
+struct RowCopy { char* dst; const char* src; ptrdiff_t dst_pitch, src_pitch; size_t row_bytes; int rows; };
+
+class CopyPool {
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable wake_, done_;
+    const std::vector<RowCopy>* jobs_ = nullptr;
+    std::atomic<size_t> next_{ 0 };
+    size_t total_ = 0;
+    int active_ = 0;
+    uint64_t generation_ = 0;
+    bool stop_ = false;
+    static constexpr int kRowsPerPiece = 64;
+
+    static void copy_piece(const RowCopy& c, int r0, int r1)
+    {
+        for (int y = r0; y < r1; ++y) std::memcpy(c.dst + (ptrdiff_t)y * c.dst_pitch, c.src + (ptrdiff_t)y * c.src_pitch, c.row_bytes);
+    }
+    // pieces are numbered across all jobs: job j contributes ceil(rows / kRowsPerPiece) of them
+    void drain(const std::vector<RowCopy>& jobs, const std::vector<size_t>& first_piece)
+    {
+        for (;;) {
+            const size_t piece = next_.fetch_add(1, std::memory_order_relaxed);
+            if (piece >= total_) return;
+            const size_t j = (size_t)(std::upper_bound(first_piece.begin(), first_piece.end(), piece) - first_piece.begin()) - 1;
+            const int r0 = (int)(piece - first_piece[j]) * kRowsPerPiece;
+            copy_piece(jobs[j], r0, std::min(jobs[j].rows, r0 + kRowsPerPiece));
+        }
+    }
+    std::vector<size_t> first_piece_;
+    void worker()
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                wake_.wait(lk, [&] { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+            }
+            drain(*jobs_, first_piece_);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--active_ == 0) done_.notify_all();
+            }
+        }
+    }
+public:
+    explicit CopyPool(int threads)
+    {
+        for (int i = 0; i < threads; ++i) workers_.emplace_back([this] { worker(); });
+    }
+    ~CopyPool()
+    {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        wake_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    // Runs every copy of `jobs`; returns when all are done. One caller at a time (the context lock is held).
+    void run(const std::vector<RowCopy>& jobs)
+    {
+        if (jobs.empty()) return;
+        first_piece_.assign(jobs.size() + 1, 0);
+        size_t bytes = 0;
+        for (size_t j = 0; j < jobs.size(); ++j) {
+            first_piece_[j + 1] = first_piece_[j] + (size_t)(jobs[j].rows + kRowsPerPiece - 1) / kRowsPerPiece;
+            bytes += jobs[j].row_bytes * (size_t)jobs[j].rows;
+        }
+        total_ = first_piece_.back();
+        first_piece_.pop_back();
+        next_.store(0, std::memory_order_relaxed);
+        if (workers_.empty() || bytes < (size_t)1 << 20) { drain(jobs, first_piece_); return; }     // small: not worth waking anyone
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            jobs_ = &jobs;
+            active_ = (int)workers_.size();
+            ++generation_;
+        }
+        wake_.notify_all();
+        drain(jobs, first_piece_);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return active_ == 0; });
+    }
+};
 
 struct DevBuf {
     void* p = nullptr;
@@ -135,6 +229,16 @@ struct sn_ctx {
     sn_stats stats{};
     std::string error;
     std::mutex mu;
+    std::unique_ptr<CopyPool> copy_pool;   // created on the first staged (pageable) transfer
+    CopyPool& pool()
+    {
+        if (!copy_pool) {
+            const char* v = getenv("SANGNOM_B200_COPY_THREADS");
+            int n = v && *v ? atoi(v) : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+            copy_pool.reset(new CopyPool(std::max(0, std::min(n, 64) - 1)));      // the caller is one of the n
+        }
+        return *copy_pool;
+    }
 
     int fail(int code, const char* fmt, ...)
     {
@@ -300,12 +404,10 @@ sn::PlaneTask make_task(const sn_ctx* ctx, const Pass& p, void* plane, size_t pi
     return t;
 }
 
-void host_copy_plane(const sn_plane_job& jb, int sb)
+void host_copy_plane(const sn_plane_job& jb, int sb, std::vector<RowCopy>& copies)
 {
     if (jb.src == jb.dst) return;
-    const size_t row = (size_t)jb.width * sb;
-    for (int y = 0; y < jb.dst_height; ++y)
-        std::memcpy(static_cast<char*>(jb.dst) + (ptrdiff_t)y * jb.dst_pitch, static_cast<const char*>(jb.src) + (ptrdiff_t)y * jb.src_pitch, row);
+    copies.push_back(RowCopy{ static_cast<char*>(jb.dst), static_cast<const char*>(jb.src), jb.dst_pitch, jb.src_pitch, (size_t)jb.width * sb, jb.dst_height });
 }
 
 // Launch the passes of a set of frames: one kernel per pass index (all first planes, then all
@@ -377,14 +479,15 @@ int drain_slot(sn_ctx* ctx, Slot& s)
                 s.frames.size(), t0, t1, t2, t3, t4, t5);
     }
     const int sb = ctx->sample_bytes;
+    std::vector<RowCopy> copies;
     for (FramePlan* f : s.frames)
         for (Pass& p : f->passes) {
             if (p.down != Pass::STAGED) continue;
             const sn_plane_job& jb = *p.job;
-            const size_t row = (size_t)p.W * sb;
             const char* st = static_cast<const char*>(s.stage_out.p) + p.stage_out_off;
-            for (int y = 0; y < p.H; ++y) std::memcpy(static_cast<char*>(jb.dst) + (ptrdiff_t)y * jb.dst_pitch, st + (size_t)y * p.dst_pitch, row);
+            copies.push_back(RowCopy{ static_cast<char*>(jb.dst), st, jb.dst_pitch, (ptrdiff_t)p.dst_pitch, (size_t)p.W * sb, p.H });
         }
+    if (!copies.empty()) ctx->pool().run(copies);
     s.frames.clear();
     s.busy = false;
     return SN_OK;
@@ -755,13 +858,30 @@ int submit_locked(sn_ctx* ctx, const sn_plane_job* user_jobs, int njobs, uint64_
             break;
         }
 
+        // ---- host-side copies of the chunk, all at once on the copy pool: kept rows of pageable sources into the
+        // pinned staging buffer, and the planes that are only copied (disabled planes, alpha) ----
+        {
+            std::vector<RowCopy> host_copies;
+            for (size_t k = first; k < last; ++k) {
+                FramePlan& f = frames[k];
+                for (const sn_plane_job* c : f.copies) host_copy_plane(*c, sb, host_copies);
+                for (Pass& p : f.passes) {
+                    if (p.up != Pass::STAGED) continue;
+                    const sn_plane_job& jb = *p.job;
+                    const char* kept = static_cast<const char*>(jb.src) + (jb.mode == SN_MODE_FIELD ? (ptrdiff_t)jb.offset * jb.src_pitch : 0);
+                    const ptrdiff_t kept_step = jb.src_pitch * (jb.mode == SN_MODE_FIELD ? 2 : 1);
+                    host_copies.push_back(RowCopy{ static_cast<char*>(s.stage_in.p) + p.stage_in_off, kept, (ptrdiff_t)p.src_pitch, kept_step, (size_t)p.W * sb, p.n });
+                }
+            }
+            if (!host_copies.empty()) ctx->pool().run(host_copies);
+        }
+
         cudaEventRecord(s.h2d_start, ctx->h2d);
         // ---- upload (the reference's kept-field BitBlt, SangNom2.cpp:361-377, becomes DMA + the kernel's own reads) ----
         std::vector<std::vector<sn::PlaneTask>> by_pass;
         std::vector<Segment> up_segs, down_segs;
         for (size_t k = first; k < last && status == SN_OK; ++k) {
             FramePlan& f = frames[k];
-            for (const sn_plane_job* c : f.copies) host_copy_plane(*c, sb);
             place_state(ctx, f, static_cast<char*>(s.state.p) + f.state_off);
             for (size_t q = 0; q < f.passes.size(); ++q) {
                 Pass& p = f.passes[q];
@@ -772,9 +892,7 @@ int submit_locked(sn_ctx* ctx, const sn_plane_job* user_jobs, int njobs, uint64_
                 char* dsrc = static_cast<char*>(s.planes.p) + p.src_off;
                 e = cudaSuccess;
                 if (p.up == Pass::STAGED) {
-                    char* st = static_cast<char*>(s.stage_in.p) + p.stage_in_off;
-                    for (int y = 0; y < p.n; ++y) std::memcpy(st + (size_t)y * p.src_pitch, kept + (size_t)y * kept_step, row);
-                    add_segment(up_segs, st, dsrc, p.src_bytes, -1);                         // the slot's own staging buffer
+                    add_segment(up_segs, static_cast<char*>(s.stage_in.p) + p.stage_in_off, dsrc, p.src_bytes, -1);                         // the slot's own staging buffer
                 } else if (p.up == Pass::LINEAR) {
                     add_segment(up_segs, const_cast<void*>(jb.src), dsrc, p.src_bytes, p.src_pinned);
                 } else {

@@ -21,6 +21,8 @@
 #include <cstdarg>
 #include <cstddef>
 #include <cstdint>
+#include <mutex>
+#include <vector>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -120,11 +122,41 @@ struct VideoInfo {
 
 // ---------------------------------------------------------------------------------------------
 // Frames. One heap block per plane; pitch rounded up to the requested alignment.
+// Plane buffers are recycled through a small free list, like AviSynth+'s frame registry: a frame server does not
+// go to the system allocator (and fault in fresh pages) for every output frame.
+class StubFramePool {
+    struct Entry { void* p; size_t bytes, align; };
+    static std::mutex& mu() { static std::mutex m; return m; }
+    static std::vector<Entry>& list() { static std::vector<Entry> v; return v; }
+public:
+    static void* take(size_t bytes, size_t align)
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu());
+            auto& v = list();
+            for (size_t i = 0; i < v.size(); ++i)
+                if (v[i].bytes == bytes && v[i].align == align) { void* p = v[i].p; v[i] = v.back(); v.pop_back(); return p; }
+        }
+        void* mem = nullptr;
+        if (::posix_memalign(&mem, align, bytes ? bytes : 1) != 0) throw std::bad_alloc();
+        return mem;
+    }
+    static void give(void* p, size_t bytes, size_t align)
+    {
+        std::lock_guard<std::mutex> lk(mu());
+        auto& v = list();
+        if (v.size() < 4096) v.push_back(Entry{ p, bytes, align }); else std::free(p);
+    }
+};
+
 class VideoFrame {
     friend class PVideoFrame;
     friend class FakeHostAccess;
     int refcount = 0;
-    struct PlaneBuf { BYTE* data = nullptr; int pitch = 0, row_size = 0, height = 0; };
+    struct PlaneBuf { BYTE* data = nullptr; int pitch = 0, row_size = 0, height = 0; size_t bytes = 0, align = 0; };
+    // buffers go back to the pool of the module that created the frame (this header is compiled into several shared
+    // objects, each with its own StubFramePool statics; the destructor may run in any of them)
+    void (*release_)(void*, size_t, size_t) = nullptr;
     PlaneBuf planes_[4];
     std::vector<std::pair<std::string, int64_t>> props_;
 
@@ -143,6 +175,7 @@ public:
         const int n = vi.NumComponents();
         static const int ids[4] = { PLANAR_Y, PLANAR_U, PLANAR_V, PLANAR_A };
         if (align < 16) align = 16;
+        release_ = &StubFramePool::give;
         for (int i = 0; i < n; ++i) {
             PlaneBuf& p = planes_[i];
             const int sw = (i == 1 || i == 2) ? vi.GetPlaneWidthSubsampling(ids[i]) : 0;
@@ -150,15 +183,16 @@ public:
             p.row_size = (vi.width >> sw) * vi.ComponentSize();
             p.height = vi.height >> sh;
             p.pitch = (p.row_size + align - 1) / align * align;
-            void* mem = nullptr;
-            if (::posix_memalign(&mem, (size_t)align, (size_t)p.pitch * (size_t)std::max(p.height, 1)) != 0) throw std::bad_alloc();
-            p.data = static_cast<BYTE*>(mem);
+            const size_t bytes = (size_t)p.pitch * (size_t)std::max(p.height, 1);
+            p.data = static_cast<BYTE*>(StubFramePool::take(bytes, (size_t)align));
+            p.bytes = bytes; p.align = (size_t)align;
             // New frames hold garbage in a real host; poison them so that reads of never-written
-            // output (e.g. the alpha plane in the reference) are visible in tests.
-            std::memset(p.data, poison ? 0xCD : 0, (size_t)p.pitch * (size_t)std::max(p.height, 1));
+            // output (e.g. the alpha plane in the reference) are visible in tests. Without poisoning the
+            // memory is left as it is, like a real host's recycled frame buffers.
+            if (poison) std::memset(p.data, 0xCD, bytes);
         }
     }
-    ~VideoFrame() { for (auto& p : planes_) std::free(p.data); }
+    ~VideoFrame() { for (auto& p : planes_) if (p.data) release_(p.data, p.bytes, p.align); }
     VideoFrame(const VideoFrame&) = delete;
     VideoFrame& operator=(const VideoFrame&) = delete;
 

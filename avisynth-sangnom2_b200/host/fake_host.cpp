@@ -112,15 +112,18 @@ public:
     std::vector<int> requests;   // log of GetFrame(n) calls, for the batching tests
     std::mutex mu;
 
-    SourceClip(const VideoInfo& v, int pm) : vi(v), parity_mode(pm) {
-        frames.resize((size_t)v.num_frames);
+    bool log_requests = true;
+    // stored < num_frames: a long clip that repeats its `stored` frames (for throughput runs)
+    SourceClip(const VideoInfo& v, int pm, int stored = 0) : vi(v), parity_mode(pm) {
+        frames.resize((size_t)(stored > 0 ? stored : v.num_frames));
         for (auto& f : frames) f = PVideoFrame(new VideoFrame(vi, FRAME_ALIGN, false));
+        log_requests = stored <= 0;
     }
     PVideoFrame __stdcall GetFrame(int n, IScriptEnvironment*) override {
         std::lock_guard<std::mutex> lk(mu);
-        requests.push_back(n);
+        if (log_requests) requests.push_back(n);
         n = std::max(0, std::min(n, vi.num_frames - 1));
-        return frames[(size_t)n];
+        return frames[(size_t)n % frames.size()];
     }
     bool __stdcall GetParity(int n) override {
         switch (parity_mode) {
@@ -197,10 +200,23 @@ void* fh_source_create(int width, int height, int components, int sub_w, int sub
     return h;
 }
 
+// A clip of `num_frames` frames that repeats `stored` distinct ones (frame n shows stored frame n % stored).
+void* fh_source_create_looped(int width, int height, int components, int sub_w, int sub_h, int bits,
+                              int is_rgb, int is_planar, int stored, int num_frames, int parity_mode) {
+    VideoInfo vi;
+    vi.width = width; vi.height = height; vi.num_frames = num_frames;
+    vi.stub_components = components; vi.stub_sub_w = sub_w; vi.stub_sub_h = sub_h; vi.stub_bits = bits;
+    vi.stub_rgb = is_rgb != 0; vi.stub_planar = is_planar != 0;
+    auto* h = new ClipHandle();
+    h->source = new SourceClip(vi, parity_mode, stored);
+    h->clip = PClip(h->source);
+    return h;
+}
+
 // Copy one plane of frame n into the source clip (src_pitch in bytes).
 int fh_source_set_plane(void* clip, int n, int plane_index, const void* data, int src_pitch) {
     auto* h = static_cast<ClipHandle*>(clip);
-    if (!h->source || n < 0 || n >= h->source->vi.num_frames) return -1;
+    if (!h->source || n < 0 || n >= (int)h->source->frames.size()) return -1;
     VideoFrame* f = h->source->frames[(size_t)n].operator->();
     const int id = kPlaneIds[plane_index];
     BYTE* d = f->GetWritePtr(id);
@@ -211,7 +227,7 @@ int fh_source_set_plane(void* clip, int n, int plane_index, const void* data, in
 
 int fh_source_set_prop(void* clip, int n, const char* key, long long value) {
     auto* h = static_cast<ClipHandle*>(clip);
-    if (!h->source || n < 0 || n >= h->source->vi.num_frames) return -1;
+    if (!h->source || n < 0 || n >= (int)h->source->frames.size()) return -1;
     h->source->frames[(size_t)n]->stub_set_prop(key, value);
     return 0;
 }

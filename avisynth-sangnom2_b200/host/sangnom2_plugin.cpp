@@ -10,6 +10,7 @@
 // create a context the filter constructor raises a script error.
 #include "sangnom2_filter.h"
 
+#include <algorithm>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -52,7 +53,11 @@ SangNom2::SangNom2(PClip _child, int order, int aa, int aac, int threads, bool d
     cfg.sample_type = sample_bytes_;
     cfg.pool_width = vi.width;       // pool geometry comes from the OUTPUT luma size (:287-288)
     cfg.pool_height = vi.height;
-    batch_frames_ = env_int("SANGNOM_B200_BATCH", 8, 1, 256);
+    // frames fetched and processed per cache miss on sequential access: enough to keep the device pipeline busy, but
+    // bounded by the memory the finished frames occupy until they are served (about 128 MB per batch by default)
+    const long long frame_bytes = (long long)vi.width * vi.height * sample_bytes_ * (plane_count_ == 1 ? 2 : 3) / 2 + 1;
+    const int default_batch = (int)std::max(4LL, std::min(32LL, (128LL << 20) / frame_bytes));
+    batch_frames_ = env_int("SANGNOM_B200_BATCH", default_batch, 1, 256);
     cfg.max_frames_in_flight = batch_frames_ < 3 ? 3 : batch_frames_;
     // SANGNOM_B200_PERSISTENT=1: keep the scratch-pool state from frame to frame like one long-lived reference
     // instance (bit-compatible with a sequential single-instance reference run where that is not frame-pure:

@@ -204,6 +204,16 @@ class FakeHost:
         self._clips.append(c)
         return c
 
+    def looped_source(self, width, height, fmt: ClipFormat, stored, num_frames, parity_mode=2):
+        """A long clip that repeats its `stored` frames (set_frame(0..stored-1)); for throughput runs."""
+        L = _load()
+        L.fh_source_create_looped.restype, L.fh_source_create_looped.argtypes = C.c_void_p, [C.c_int] * 11
+        h = L.fh_source_create_looped(width, height, fmt.components, fmt.sub_w, fmt.sub_h, fmt.bits,
+                                      int(fmt.rgb), int(fmt.planar), stored, num_frames, parity_mode)
+        c = Clip(self, h, fmt, True)
+        self._clips.append(c)
+        return c
+
     def invoke(self, func, clip, **kwargs):
         names = (C.c_char_p * max(1, len(kwargs)))(*[k.encode() for k in kwargs])
         vals = (C.c_int * max(1, len(kwargs)))(*[int(v) for v in kwargs.values()])

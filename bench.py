@@ -396,6 +396,7 @@ def run_ours(args):
     e2e_sync_value = Fe * world * esteps / float(t_e[1].item())
     e2e_field_value = Fe * world * esteps / float(t_e[2].item()) if field_s else None
     clocks = sampler.stop() if rank == 0 else None
+    plugin_leg = plugin_fps(wl, args.plugin_seconds) if (rank == 0 and world == 1 and args.plugin_seconds > 0) else None
 
     if rank == 0:
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -424,6 +425,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": est["d2h_bytes"] // esteps, "steps": esteps,
                     "api": "sangnom_cuda_submit/_wait, two steps in flight, pinned host arenas",
                     "sync_call_value": e2e_sync_value,
+                    "plugin_value": plugin_leg,
                     "field_input": None if e2e_field_value is None else {
                         "value": e2e_field_value, "h2d_bytes_per_step": fst["h2d_bytes"] // esteps, "d2h_bytes_per_step": fst["d2h_bytes"] // esteps,
                         "note": "separated-field input (SN_MODE_DH): same output frames, half the upload"}},
@@ -446,6 +448,45 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def plugin_fps(wl, seconds):
+    """The drop-in path itself: our AviSynth plugin pulled frame by frame through the fake host (PAGEABLE host frames,
+    one filter instance, sequential GetFrame) - the same harness the reference arm is timed with."""
+    from pysangnom.clips import make_frame
+    from pysangnom.fakehost import FORMATS, FakeHost
+    from pysangnom import fakehost as fh
+    fmtname, w, h, kw, _, _ = WORKLOADS[wl]
+    fmt = FORMATS[fmtname]
+    ours = os.path.join(PKG, "libsangnom2_b200.so")
+    nsrc, total = 8, 100000
+    host = FakeHost(poison_new_frames=False)
+    try:
+        host.load_plugin(ours)
+        src = host.looped_source(w, h, fmt, nsrc, total, parity_mode=2)
+        for i in range(nsrc):
+            src.set_frame(i, make_frame(1, w, h, fmt, "noise", i))
+        flt = host.invoke("SangNom2", src, **kw)
+        L = fh._load()
+        err = C.create_string_buffer(256)
+
+        def pull(n):
+            f = L.fh_get_frame(host.env, flt.handle, n, err, 256)
+            if not f:
+                raise RuntimeError(err.value.decode())
+            L.fh_frame_release(f)
+
+        n = 0
+        while n < 96:
+            pull(n); n += 1
+        t0, n0 = time.perf_counter(), n
+        while time.perf_counter() - t0 < seconds and n < total:
+            pull(n); n += 1
+        dt = time.perf_counter() - t0
+        return {"value": (n - n0) / dt, "unit": "frames/s", "frames": n - n0,
+                "note": "our AviSynth plugin through the fake host: pageable frames, one instance, sequential GetFrame"}
+    finally:
+        host.close()
 
 
 def cpu_port_baseline(wl, seconds):
@@ -477,6 +518,7 @@ def main():
     ap.add_argument("--in-flight", type=int, default=0, help="frames resident on the device in the host path (0 = library default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--plugin-seconds", type=float, default=2.0, help="seconds of the plugin-path leg (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
