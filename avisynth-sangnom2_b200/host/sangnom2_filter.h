@@ -9,6 +9,7 @@
 
 #include <map>
 #include <mutex>
+#include <vector>
 
 #include "avisynth.h"
 #include "sangnom_cuda.h"
@@ -26,11 +27,22 @@ class SangNom2 : public GenericVideoFilter {
     sn_ctx* ctx_ = nullptr;
     int batch_frames_;        // frames fetched and processed per cache miss on sequential access
     int last_request_ = -2;
+    bool prefetch_ = true;    // submit the next batch while the host consumes the finished one
     std::map<int, PVideoFrame> ready_;   // finished frames not yet (or recently) served
     std::mutex mu_;
 
+    // A batch that has been submitted to the device but not waited for yet: while the host consumes the frames of
+    // batch k, batch k+1 is already uploading / running (sangnom_cuda_submit / _wait).
+    struct Pending {
+        bool active = false;
+        int first = 0, count = 0;
+        sn_ticket ticket = 0;
+        std::vector<PVideoFrame> srcs, dsts;   // keep the frame buffers alive until the batch is waited for
+    } pending_;
+
     int field_offset(int n);
-    void process_batch(int first, int count, IScriptEnvironment* env);
+    void start_batch(int first, int count, IScriptEnvironment* env);
+    void finish_batch(IScriptEnvironment* env);
 
 public:
     SangNom2(PClip _child, int order, int aa, int aac, int threads, bool dh, bool luma, bool chroma, int opt, IScriptEnvironment* env);

@@ -64,12 +64,16 @@ SangNom2::SangNom2(PClip _child, int order, int aa, int aac, int threads, bool d
     // widths that are not a multiple of 32, luma=false with subsampled chroma). Frames then run one after another.
     if (env_int("SANGNOM_B200_PERSISTENT", 0, 0, 1)) cfg.flags |= SN_FLAG_PERSISTENT_POOL;
     if (opt == 1) cfg.flags |= SN_FLAG_SATURATE;
+    // SANGNOM_B200_PREFETCH=0: no speculative next batch (every child frame is requested only when it is needed)
+    prefetch_ = env_int("SANGNOM_B200_PREFETCH", 1, 0, 1) != 0;
     if (sangnom_cuda_create(&cfg, &ctx_) != SN_OK)
         env->ThrowError("SangNom2: %s", sangnom_cuda_last_error(nullptr));
 }
 
 SangNom2::~SangNom2()
 {
+    if (pending_.active) sangnom_cuda_wait(ctx_, pending_.ticket);     // nothing may still write into the frames
+    pending_ = Pending{};
     ready_.clear();
     sangnom_cuda_destroy(ctx_);
 }
@@ -84,9 +88,12 @@ int SangNom2::field_offset(int n)
     }
 }
 
-void SangNom2::process_batch(int first, int count, IScriptEnvironment* env)
+void SangNom2::start_batch(int first, int count, IScriptEnvironment* env)
 {
-    std::vector<PVideoFrame> srcs((size_t)count), dsts((size_t)count);
+    std::vector<PVideoFrame>& srcs = pending_.srcs;
+    std::vector<PVideoFrame>& dsts = pending_.dsts;
+    srcs.assign((size_t)count, PVideoFrame());
+    dsts.assign((size_t)count, PVideoFrame());
     std::vector<sn_plane_job> jobs;
     jobs.reserve((size_t)count * 5);
     for (int k = 0; k < count; ++k) {
@@ -130,31 +137,69 @@ void SangNom2::process_batch(int first, int count, IScriptEnvironment* env)
             }
         }
     }
-    if (sangnom_cuda_process_planes(ctx_, jobs.data(), (int)jobs.size()) != SN_OK)
+    // the job array is copied by the library; the frames themselves stay referenced in pending_
+    if (sangnom_cuda_submit(ctx_, jobs.data(), (int)jobs.size(), &pending_.ticket) != SN_OK) {
+        pending_ = Pending{};
         env->ThrowError("SangNom2: %s", sangnom_cuda_last_error(ctx_));
-    for (int k = 0; k < count; ++k) ready_[first + k] = dsts[k];
+    }
+    pending_.active = true;
+    pending_.first = first;
+    pending_.count = count;
+}
+
+void SangNom2::finish_batch(IScriptEnvironment* env)
+{
+    if (!pending_.active) return;
+    const int rc = sangnom_cuda_wait(ctx_, pending_.ticket);
+    if (rc == SN_OK)
+        for (int k = 0; k < pending_.count; ++k) ready_[pending_.first + k] = pending_.dsts[(size_t)k];
+    pending_ = Pending{};
+    if (rc != SN_OK) env->ThrowError("SangNom2: %s", sangnom_cuda_last_error(ctx_));
 }
 
 PVideoFrame __stdcall SangNom2::GetFrame(int n, IScriptEnvironment* env)
 {
     std::lock_guard<std::mutex> lk(mu_);
+    const int last = vi.num_frames > 0 ? vi.num_frames - 1 : n;
+    auto window = [&](int first, int want) {            // frames [first, first+count) still to compute, clip end respected
+        int count = want;
+        if (first + count - 1 > last) count = last - first + 1;
+        for (int k = 1; k < count; ++k)
+            if (ready_.count(first + k)) { count = k; break; }     // frames already finished are not recomputed
+        return count < 1 ? 0 : count;
+    };
     auto hit = ready_.find(n);
     if (hit == ready_.end()) {
-        // Sequential pulls (the normal frameserver pattern) are served in batches so the GPU sees
-        // many planes per launch; a seek falls back to a single frame.
-        const bool sequential = (n == last_request_ + 1) || (n == 0 && last_request_ == -2);
-        int count = sequential ? batch_frames_ : 1;
-        const int last = vi.num_frames > 0 ? vi.num_frames - 1 : n;
-        if (n + count - 1 > last) count = last - n + 1;
-        if (count < 1) count = 1;
-        // frames already finished inside the window are not recomputed
-        for (int k = 1; k < count; ++k)
-            if (ready_.count(n + k)) { count = k; break; }
-        process_batch(n, count, env);
+        if (pending_.active && n >= pending_.first && n < pending_.first + pending_.count) {
+            finish_batch(env);                          // the prefetched batch holds it
+        } else {
+            finish_batch(env);                          // one batch in flight at a time
+            hit = ready_.find(n);
+            if (hit == ready_.end()) {
+                // Sequential pulls (the normal frameserver pattern) are served in batches so the GPU sees
+                // many planes per launch; a seek falls back to a single frame.
+                const bool sequential = (n == last_request_ + 1) || (n == 0 && last_request_ == -2);
+                int count = window(n, sequential ? batch_frames_ : 1);
+                if (count < 1) count = 1;
+                start_batch(n, count, env);
+                finish_batch(env);
+            }
+        }
         hit = ready_.find(n);
     }
     PVideoFrame out = hit->second;
+    const bool sequential = (n == last_request_ + 1) || (n == 0 && last_request_ == -2);
     last_request_ = n;
+    // Prefetch: on a sequential read the batch after the finished run is submitted right away, so that it uploads and
+    // runs while the host consumes (encodes, filters further) what is ready.
+    if (sequential && !pending_.active && prefetch_) {
+        int next = n + 1;
+        while (ready_.count(next)) ++next;
+        if (next <= last && next - n <= batch_frames_) {
+            const int count = window(next, batch_frames_);
+            if (count > 0) start_batch(next, count, env);
+        }
+    }
     // keep a bounded window of finished frames around the read position
     while ((int)ready_.size() > 2 * batch_frames_) {
         auto lo = ready_.begin();

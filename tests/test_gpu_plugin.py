@@ -147,6 +147,7 @@ def test_filter_object_properties():
 
 def test_batched_prefetch_and_seek(monkeypatch):
     monkeypatch.setenv("SANGNOM_B200_BATCH", "4")
+    monkeypatch.setenv("SANGNOM_B200_PREFETCH", "0")
     fmt = FORMATS["Y8"]
     w, h, n = 64, 32, 10
     frames = [make_frame(6, w, h, fmt, "edges", i) for i in range(n)]
@@ -168,3 +169,31 @@ def test_batched_prefetch_and_seek(monkeypatch):
         assert src.requests()[8:] == [9]
         assert np.array_equal(flt.get_frame(8)[0], exp[8])   # backwards
         assert np.array_equal(flt.get_frame(2)[0], exp[2])
+
+
+def test_next_batch_is_prefetched_asynchronously(monkeypatch):
+    """Default mode: after a sequential miss the following batch is submitted at once (sangnom_cuda_submit) and waited
+    for only when one of its frames is pulled; seeks, the clip end and the filter's destruction with a batch in flight
+    all keep the output exact."""
+    monkeypatch.setenv("SANGNOM_B200_BATCH", "4")
+    fmt = FORMATS["YUV420P8"]
+    w, h, n = 96, 64, 19
+    frames = [make_frame(8, w, h, fmt, "noise", i) for i in range(n)]
+    exp = [O.oracle_frame(fr, 8, order=0, aa=48, aac=48, parity=parity_of(i)) for i, fr in enumerate(frames)]
+    with FakeHost() as host:
+        host.load_plugin(OURS)
+        src = host.source(w, h, fmt, n, parity_mode=2)
+        for i, fr in enumerate(frames):
+            src.set_frame(i, fr)
+        flt = host.invoke("SangNom2", src, order=0, aa=48, aac=48)
+        assert_planes_equal(flt.get_frame(0)[:3], exp[0][:3], "frame 0")
+        assert src.requests() == [0, 1, 2, 3, 4, 5, 6, 7]          # batch 0 finished, batch 1 already in flight
+        for i in range(1, 9):
+            assert_planes_equal(flt.get_frame(i)[:3], exp[i][:3], f"frame {i}")
+        assert sorted(set(src.requests())) == list(range(16))      # pulling frame 4 waited for batch 1 and started batch 2, frame 8 batch 3
+        assert_planes_equal(flt.get_frame(17)[:3], exp[17][:3], "seek forward")          # with a batch pending
+        assert_planes_equal(flt.get_frame(18)[:3], exp[18][:3], "last frame")
+        assert_planes_equal(flt.get_frame(3)[:3], exp[3][:3], "seek back")
+        for i in range(4, 12):
+            assert_planes_equal(flt.get_frame(i)[:3], exp[i][:3], f"frame {i} again")
+        # leave with a batch in flight: the destructor must wait for it
