@@ -209,6 +209,30 @@ def run_reference(args):
     return 0
 
 
+_ORIGINAL_AFFINITY = None
+
+
+def bind_to_gpu_numa_node(gpu_index):
+    """Run this rank on the CPUs next to its GPU so that the pinned staging memory it allocates (first touch) and the
+    copy threads sit on the GPU's NUMA node; matters for the end-to-end leg with several ranks per box."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        global _ORIGINAL_AFFINITY
+        _ORIGINAL_AFFINITY = os.sched_getaffinity(0)
+        cpus &= _ORIGINAL_AFFINITY
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception as e:       # no NVML / not permitted: stay where the launcher put us
+        log(f"bench: no NUMA binding ({e})")
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -227,6 +251,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libsangnom_cuda has no CPU path")
     torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cuda.load()
@@ -432,6 +457,8 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
+            if _ORIGINAL_AFFINITY:
+                os.sched_setaffinity(0, _ORIGINAL_AFFINITY)      # the CPU baseline gets every host core
             cores = len(os.sched_getaffinity(0))
             ref = reference_fps(wl, cores, args.cpu_seconds)
             if ref is not None:
