@@ -276,15 +276,19 @@ class PinnedLookup {
     GetAttr get_ = nullptr;
     std::vector<HostRange> known_;
 public:
-    PinnedLookup()
+    static GetAttr driver_entry()          // looked up once per process
     {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            get_ = reinterpret_cast<GetAttr>(fn);
-        else
+        static const GetAttr fn = [] {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+                return reinterpret_cast<GetAttr>(p);
             cudaGetLastError();
+            return static_cast<GetAttr>(nullptr);
+        }();
+        return fn;
     }
+    PinnedLookup() : get_(driver_entry()) {}
     // 0 = pageable; otherwise 1 + index of the allocation (stable for this object's lifetime)
     int find(const void* p)
     {
