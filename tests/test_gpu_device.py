@@ -74,7 +74,8 @@ def test_device_path_matches_oracle(cuda, fmtname, w, h, mode):
 
 
 FULL = [("YUV420P8", 1920, 1080, dict(order=0, aa=48, aac=48)), ("YUV420PS", 3840, 2160, dict(order=2, aa=48, aac=24)),
-        ("YUV420P10", 3840, 2160, dict(order=1, aa=48, aac=48)), ("YUV444P16", 1920, 2160, dict(order=1, aa=48))]
+        ("YUV420P10", 3840, 2160, dict(order=1, aa=48, aac=48)), ("YUV444P16", 1920, 2160, dict(order=1, aa=48)),
+        ("Y8", 7680, 4320, dict(order=1, aa=48))]
 
 
 @pytest.mark.parametrize("fmtname,w,h,kw", FULL, ids=[f[0] + f"_{f[1]}x{f[2]}" for f in FULL])
@@ -85,12 +86,13 @@ def test_full_size_properties(cuda, fmtname, w, h, kw):
     (3) a clip that is constant along x interpolates to the plain vertical mean (all nine costs tie, so
         buffer 4 wins, reference SangNom2.cpp:214-217)."""
     fmt = FORMATS[fmtname]
+    np_ = min(fmt.components, 3)
     frames = [make_frame(17, w, h, fmt, "noise", i) for i in range(2)]
     got, _ = device_frames(cuda, fmt, w, h, frames, **kw)
     alone, _ = device_frames(cuda, fmt, w, h, frames[1:], **kw) if kw["order"] != 0 else (None, None)
     for i, fr in enumerate(frames):
         off = cuda.resolve_offset(kw["order"], parity_of(i))
-        for p in range(3):
+        for p in range(np_):
             src, out = fr[p], got[i][p]
             assert np.array_equal(out[off::2], src[off::2])
             if off == 0:
@@ -98,14 +100,14 @@ def test_full_size_properties(cuda, fmtname, w, h, kw):
             else:
                 assert np.array_equal(out[0], out[1])
     if alone is not None:
-        for p in range(3):
+        for p in range(np_):
             assert np.array_equal(alone[0][p].view(np.uint8), got[1][p].view(np.uint8))
     # (3)
     col = make_frame(19, 8, h, fmt, "noise", 0)
     flat = [np.repeat(pl[:, :1], fmt.plane_shape(w, h, p)[1], axis=1) for p, pl in enumerate(col)]
     out, _ = device_frames(cuda, fmt, w, h, [flat], **kw)
     off = cuda.resolve_offset(kw["order"], True)
-    for p in range(3):
+    for p in range(np_):
         kept = out[0][p][off::2]
         mid = out[0][p][off + 1::2][:len(kept) - 1]
         if fmt.bits == 32:
@@ -116,3 +118,16 @@ def test_full_size_properties(cuda, fmtname, w, h, kw):
         else:
             exp = ((kept[:-1].astype(np.int64) + kept[1:] + 1) >> 1).astype(mid.dtype)
             assert np.array_equal(mid, exp)
+
+
+@pytest.mark.parametrize("fmtname,w,h,kw", [("Y8", 7680, 4320, dict(order=2, aa=48)), ("YUV420P8", 1920, 1080, dict(order=0, aa=48, aac=48)),
+                                            ("Y16", 8192, 256, dict(order=1, aa=48)), ("Y32", 8192, 128, dict(order=1, aa=48))],
+                         ids=["cfg5a_8k_y8", "cfg2_1080p", "widest_u16", "widest_f32"])
+def test_full_size_against_oracle(cuda, fmtname, w, h, kw):
+    """One frame at BASELINE.json's largest sizes and at the widest planes the kernels accept (8-block clusters),
+    bit-exact against the oracle."""
+    fmt = FORMATS[fmtname]
+    fr = make_frame(23, w, h, fmt, "noise", 0)
+    got, _ = device_frames(cuda, fmt, w, h, [fr], mode="field", **kw)
+    exp = O.oracle_frame(fr, fmt.bits, parity=True, **kw)
+    assert_planes_equal(got[0], exp[:len(got[0])], f"{fmtname} {w}x{h}")
