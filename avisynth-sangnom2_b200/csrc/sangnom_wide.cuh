@@ -203,6 +203,9 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
 #pragma unroll
     for (int e = 0; e < kWin; ++e) { wa[e] = wb[e]; wb[e] = wc[e]; }
 
+    // all blocks of a cluster run before the first DSMEM store
+    if constexpr (kClustered) cl::sync_all();
+
     const int tkey = (int)min((long long)t.thr_i + 1, 0x7FFFFFFLL) << 4;      // (thr+1) << 4: "every cost above the threshold"
     const bool exporting = t.out.a != nullptr || t.out.b != nullptr;
 

@@ -262,6 +262,8 @@ def run_ours(args):
     sb = fmt.sample_bytes
     F = args.frames or DEFAULT_FRAMES[wl]                 # frames per step per GPU (weak scaling)
     Fe = args.e2e_frames or E2E_FRAMES[wl]
+    if world > 1 and not args.e2e_frames:
+        Fe = max(8, Fe // 2)                               # several ranks share the host: half the pinned staging per rank
     first, _ = frame_range(F * world, rank, world)        # this rank's contiguous frame range of the global clip
     nplanes = min(fmt.components, 3)
     proc = [kw.get("luma", True)] + [kw.get("chroma", True)] * 2
