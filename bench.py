@@ -190,7 +190,7 @@ def run_reference(args):
     for _ in range(args.steps):
         res = reference_fps(wl, cores, per_step)
         if res is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (no /root/reference in the build container)"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref was not built (no /root/reference in the build container)"})
             return 0
         vals.append(res["fps"])
         total += res["frames"]
@@ -205,7 +205,7 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
     }
-    print(json.dumps(out))
+    emit(out)
     return 0
 
 
@@ -471,7 +471,7 @@ def run_ours(args):
                                        "opt0_cpp_path_fps": ref0["fps"]}
             else:
                 out["cpu_baseline"] = cpu_port_baseline(wl, args.cpu_seconds)
-        print(json.dumps(out))
+        emit(out)
     ctx.close()
     ectx.close()
     if world > 1:
@@ -549,9 +549,26 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--plugin-seconds", type=float, default=2.0, help="seconds of the plugin-path leg (0 = skip)")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: anything a library prints there meanwhile (NCCL's version
+    # banner, for one) is sent to stderr
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
+
+
+_RESULT_FD = None
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
 
 
 if __name__ == "__main__":
