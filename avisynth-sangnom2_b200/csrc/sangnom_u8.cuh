@@ -396,6 +396,15 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
             M[i][2] = lanes_lo(Pb[i][1]) + leak(i); M[i][3] = lanes_hi(Pb[i][1]) + leak(i);
         }
     }
+    // Threads without (all) pixel columns read the cost state the previous pass handed over. Those loads would open
+    // every row and stall it for a DRAM round trip, so they run one row ahead: sp holds pool row r+1 at the top of row r.
+#ifdef SN_HOST_EMULATION
+    const bool warp_full = npix == kCols;
+#else
+    const bool warp_full = __all_sync(0xFFFFFFFFu, npix == kCols);
+#endif
+    uint32_t sp[kNumCost][2];
+    if (!warp_full) stale_costs(2, sp);
     // all blocks of a cluster run before the first DSMEM store
     if constexpr (kClustered) cl::sync_all();
 
@@ -425,7 +434,12 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
         uint2* const Lrow = Lbase + ((size_t)(r & 1) * (T + 2) + 1 + tid) * kLEntry;      // my entry
         {
             uint32_t Pb[kNumCost][2];
-            if (!kFull || !kPair) stale_costs(r + 1, Pb);
+            if constexpr (!kFull) {
+#pragma unroll
+                for (int i = 0; i < kNumCost; ++i) { Pb[i][0] = sp[i][0]; Pb[i][1] = sp[i][1]; }
+            } else if constexpr (!kPair) {
+                stale_costs(r + 1, Pb);
+            }
             if (kPair && pixels) {
                 uint32_t wc[4];
                 Taps Tc;
@@ -475,6 +489,7 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
             }
         }
         if constexpr (kClustered) cl::sync_all(); else __syncthreads();
+        if constexpr (!kFull) stale_costs(r + 2, sp);       // next row's handed-over state: in flight during phase B
 
         // ---- per cost: 7-tap sum, key = (B << 4) | rank, M = P[r+1] + B (+ leak), min over the keys ----
         uint32_t kmin[4] = { tkey, tkey, tkey, tkey };
@@ -558,11 +573,6 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
         }
     };
     // warp-uniform choice, so that a warp never splits over the two copies of the row barrier
-#ifdef SN_HOST_EMULATION
-    const bool warp_full = npix == kCols;
-#else
-    const bool warp_full = __all_sync(0xFFFFFFFFu, npix == kCols);
-#endif
     if (warp_full) sweep(std::true_type{}); else sweep(std::false_type{});
 }
 
