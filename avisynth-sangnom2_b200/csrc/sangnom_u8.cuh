@@ -495,12 +495,18 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
         uint32_t kmin[4] = { tkey, tkey, tkey, tkey };
         uint32_t held[4];
         uint8_t* outp = out.p;
+        // the four L words of a cost are fetched one cost ahead of their use, so that the shared-memory latency of
+        // cost i+1 runs under the arithmetic of cost i
+        uint2 nlh = Lrow[1 - kLEntry], noa = Lrow[0], nob = Lrow[1], nrh = Lrow[kLEntry];
 #pragma unroll
         for (int i = 0; i < kNumCost; ++i) {
-            const uint2 lh = Lrow[2 * i + 1 - kLEntry];     // (l-4,l-3) (l-2,l-1)
-            const uint2 oa = Lrow[2 * i];                   // (l0,l1) (l2,l3)
-            const uint2 ob = Lrow[2 * i + 1];               // (l4,l5) (l6,l7)
-            const uint2 rh = Lrow[2 * i + kLEntry];         // (l8,l9) (l10,l11)
+            const uint2 lh = nlh;                           // (l-4,l-3) (l-2,l-1)
+            const uint2 oa = noa;                           // (l0,l1) (l2,l3)
+            const uint2 ob = nob;                           // (l4,l5) (l6,l7)
+            const uint2 rh = nrh;                           // (l8,l9) (l10,l11)
+            if (i + 1 < kNumCost) {
+                nlh = Lrow[2 * (i + 1) + 1 - kLEntry]; noa = Lrow[2 * (i + 1)]; nob = Lrow[2 * (i + 1) + 1]; nrh = Lrow[2 * (i + 1) + kLEntry];
+            }
             const uint32_t Wm2 = lh.x, Wm1 = lh.y, W0 = oa.x, W1 = oa.y, W2 = ob.x, W3 = ob.y, W4 = rh.x, W5 = rh.y;
             // Z_k = W[k-1]+W[k]+W[k+1] (even / odd triples), X_k = Z_k + W[k-2];
             // H7_k = Z_k + (X_k.hi, X_{k+1}.lo)  -> lanes (sum l[2k-3..2k+3], sum l[2k-2..2k+4])
