@@ -432,6 +432,7 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
 
         // ---- P[r+1], L = M + P[r+1] -> shared row; M keeps P[r+1] until B[r] is known ----
         uint2* const Lrow = Lbase + ((size_t)(r & 1) * (T + 2) + 1 + tid) * kLEntry;      // my entry
+        uint2 own_xy, own_zw;
         {
             uint32_t Pb[kNumCost][2];
             if constexpr (!kFull) {
@@ -454,14 +455,17 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
                 t3_put(r + 1, tc);
                 if (kFull) pair_costs(Tb, tb, Tc, tc, Pb); else straddle_costs(Tb, tb, Tc, tc, Pb);
             }
+            // last cost first: cost 0's own L words stay in registers for the start of phase B
 #pragma unroll
-            for (int i = 0; i < kNumCost; ++i) {
+            for (int ii = 0; ii < kNumCost; ++ii) {
+                const int i = kNumCost - 1 - ii;
                 const uint32_t P0 = lanes_lo(Pb[i][0]), P1 = lanes_hi(Pb[i][0]), P2 = lanes_lo(Pb[i][1]), P3 = lanes_hi(Pb[i][1]);
                 const uint2 Lxy = make_uint2(M[i][0] + P0 - leak(i), M[i][1] + P1 - leak(i));
                 const uint2 Lzw = make_uint2(M[i][2] + P2 - leak(i), M[i][3] + P3 - leak(i));
                 Lrow[2 * i] = Lxy;
                 Lrow[2 * i + 1] = Lzw;
                 M[i][0] = P0; M[i][1] = P1; M[i][2] = P2; M[i][3] = P3;
+                if (i == 0) { own_xy = Lxy; own_zw = Lzw; }
             }
         }
         // the two edge threads of the segment supply what lies beyond it: the clamp of the recursion at pool columns 0
@@ -497,7 +501,7 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
         uint8_t* outp = out.p;
         // the four L words of a cost are fetched one cost ahead of their use, so that the shared-memory latency of
         // cost i+1 runs under the arithmetic of cost i
-        uint2 nlh = Lrow[1 - kLEntry], noa = Lrow[0], nob = Lrow[1], nrh = Lrow[kLEntry];
+        uint2 nlh = Lrow[1 - kLEntry], noa = own_xy, nob = own_zw, nrh = Lrow[kLEntry];
 #pragma unroll
         for (int i = 0; i < kNumCost; ++i) {
             const uint2 lh = nlh;                           // (l-4,l-3) (l-2,l-1)
