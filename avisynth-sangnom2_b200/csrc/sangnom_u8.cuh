@@ -560,15 +560,25 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
         }
     };
     // does any thread of my warp export pool row r? (warp-uniform, so the two variants of a row keep warps whole)
+    // The rows my warp exports are two ranges known up front (region B: rows b_r0..b_r1, all columns; region A: rows
+    // 1..a_rows for the warps that reach past a_x0), so the per-row question is two register compares; the task's
+    // region description is read from shared memory only for rows that are exported.
+    int ex_b0 = 1, ex_b1 = 0, ex_a1 = 0;
+    if (exporting) {
+        if (t.out.b != nullptr) { ex_b0 = t.out.b_r0; ex_b1 = t.out.b_r1; }
+        const bool mine_a = t.out.a != nullptr && x0 >= t.out.a_x0;
+#ifdef SN_HOST_EMULATION
+        const bool warp_a = mine_a;
+#else
+        const bool warp_a = __any_sync(0xFFFFFFFFu, mine_a);
+#endif
+        if (warp_a) ex_a1 = t.out.a_rows;
+    }
     auto export_row = [&](int r, StateRow& out) -> bool {
         out = StateRow{ nullptr, 0 };
-        if (!exporting) return false;
+        if (!((r >= ex_b0 && r <= ex_b1) || r <= ex_a1)) return false;
         out = state_row(t.out, r, x0, S);
-#ifdef SN_HOST_EMULATION
-        return out.p != nullptr;
-#else
-        return __any_sync(0xFFFFFFFFu, out.p != nullptr);
-#endif
+        return true;
     };
     auto sweep = [&](auto full) {
         int r = 1;
