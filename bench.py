@@ -358,7 +358,7 @@ def run_ours(args):
         arr = sets[i % 2][0]
         check(lib.sangnom_cuda_process_planes(ectx._h, arr, len(arr)))
 
-    for i in range(2):
+    for i in range(4):                                  # every pipeline slot has seen (and sized itself for) the largest chunk
         estep_sync(i)
     barrier()
     esteps = max(2, args.steps)
