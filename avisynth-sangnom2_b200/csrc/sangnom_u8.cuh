@@ -399,7 +399,9 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     // Threads without (all) pixel columns read the cost state the previous pass handed over. Those loads would open
     // every row and stall it for a DRAM round trip, so they run one row ahead: sp holds pool row r+1 at the top of row r.
 #ifdef SN_HOST_EMULATION
-    const bool warp_full = npix == kCols;
+    // the emulation has no warps: evaluate the predicate for the 32 threads this one would share a warp with
+    bool warp_full = true;
+    for (int l = tid & ~31; l < min((tid & ~31) + 32, T); ++l) warp_full = warp_full && min(max(W - (seg_x0 + l * kCols), 0), kCols) == kCols;
 #else
     const bool warp_full = __all_sync(0xFFFFFFFFu, npix == kCols);
 #endif
@@ -568,7 +570,8 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
         if (t.out.b != nullptr) { ex_b0 = t.out.b_r0; ex_b1 = t.out.b_r1; }
         const bool mine_a = t.out.a != nullptr && x0 >= t.out.a_x0;
 #ifdef SN_HOST_EMULATION
-        const bool warp_a = mine_a;
+        bool warp_a = false;
+        for (int l = tid & ~31; l < min((tid & ~31) + 32, T); ++l) warp_a = warp_a || (t.out.a != nullptr && seg_x0 + l * kCols >= t.out.a_x0);
 #else
         const bool warp_a = __any_sync(0xFFFFFFFFu, mine_a);
 #endif

@@ -184,3 +184,22 @@ def test_saturating_flavour_matches_oracle(emul, fmtname, w, h, kw, kind, cluste
         differs |= any(not np.array_equal(a, b) for a, b in zip(exp[:3], wrap[:3]))
     if fmtname in ("Y8", "YV12") and kind == "noise":
         assert differs, "case does not exercise the saturation"
+
+
+HELPER_CASES = [("YV12", 960, 24, dict(order=0, aa=48, aac=48), "noise"), ("YV12", 960, 16, dict(order=2, aa=48, aac=48), "edges"),
+                ("YUV422P8", 960, 12, dict(order=1, aa=30, aac=90), "noise"), ("YV411", 1280, 12, dict(order=1, aa=48, aac=30), "noise"),
+                ("YV12", 944, 20, dict(order=1, aa=128, aac=128), "noise"), ("YV12", 960, 8, dict(luma=False, aa=48, aac=48), "noise")]
+
+
+@pytest.mark.parametrize("fmtname,w,h,kw,kind", HELPER_CASES, ids=[f"{c[0]}_{c[1]}x{c[2]}_{i}" for i, c in enumerate(HELPER_CASES)])
+@pytest.mark.parametrize("saturate", [False, True], ids=["wrap", "sat"])
+def test_wide_subsampled_planes(emul, fmtname, w, h, kw, kind, saturate):
+    """8-bit planes wide enough that the chroma pixel threads end inside a 32-thread group (a "mixed" warp on the
+    device: pixel lanes and state-only lanes in one warp, the general variant of a row), run by the unclustered
+    instantiation as the launcher would; in place and out of place, wrapping and saturating flavour."""
+    fmt = FORMATS[fmtname]
+    for i in range(2):
+        fr = make_frame(73, w, h, fmt, kind, i)
+        got = emulate(emul, fr, fmt.bits, parity=(i == 0), out_of_place=(i == 1), saturate=saturate, **kw)
+        exp = O.oracle_frame(fr, fmt.bits, parity=(i == 0), saturate=saturate, **kw)
+        assert_planes_equal(got, exp[:3], f"wide {fmtname} {w}x{h} {kw} frame {i}")
