@@ -211,6 +211,7 @@ struct sn_ctx {
     int frames_in_flight = 0;
     cudaStream_t h2d = nullptr, d2h = nullptr, own_compute = nullptr;
     cudaEvent_t trace_base = nullptr;
+    bool trace_base_set = false;
     Slot slots[kSlots];
     int next_slot = 0;                   // slots are used round-robin, so this is also the oldest one in flight
     uint64_t last_ticket = 0;
@@ -806,7 +807,7 @@ int submit_locked(sn_ctx* ctx, const sn_plane_job* user_jobs, int njobs, uint64_
         }
 
     const auto t_planned = std::chrono::steady_clock::now();
-    cudaEventRecord(ctx->trace_base, ctx->h2d);
+    if (!ctx->trace_base_set) { cudaEventRecord(ctx->trace_base, ctx->h2d); ctx->trace_base_set = true; }     // one time origin per context
     const size_t chunk_frames = std::max<size_t>(1, (size_t)ctx->frames_in_flight / kSlots);
     size_t next = 0;
     int status = SN_OK;

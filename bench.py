@@ -215,6 +215,8 @@ _ORIGINAL_AFFINITY = None
 def bind_to_gpu_numa_node(gpu_index):
     """Run this rank on the CPUs next to its GPU so that the pinned staging memory it allocates (first touch) and the
     copy threads sit on the GPU's NUMA node; matters for the end-to-end leg with several ranks per box."""
+    if os.environ.get("SANGNOM_BENCH_NO_BIND"):
+        return None
     try:
         import pynvml
         pynvml.nvmlInit()
