@@ -24,6 +24,8 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 #include <chrono>
@@ -680,7 +682,7 @@ int sangnom_cuda_synchronize(sn_ctx* ctx)
 }
 
 // ---------------------------------------------------------------------------------------------
-int sangnom_cuda_process_planes_device(sn_ctx* ctx, const sn_plane_job* jobs, int njobs, void* cuda_stream)
+static int process_planes_device_impl(sn_ctx* ctx, const sn_plane_job* jobs, int njobs, void* cuda_stream)
 {
     if (!ctx) return SN_ERR_INVALID;
     if (njobs < 0 || (njobs > 0 && !jobs)) return ctx->fail(SN_ERR_INVALID, "bad job list");
@@ -981,7 +983,7 @@ int submit_locked(sn_ctx* ctx, const sn_plane_job* user_jobs, int njobs, uint64_
 
 extern "C" {
 
-int sangnom_cuda_submit(sn_ctx* ctx, const sn_plane_job* jobs, int njobs, sn_ticket* ticket)
+static int submit_impl(sn_ctx* ctx, const sn_plane_job* jobs, int njobs, sn_ticket* ticket)
 {
     if (!ctx) return SN_ERR_INVALID;
     if (!ticket) return ctx->fail(SN_ERR_INVALID, "null ticket pointer");
@@ -994,7 +996,7 @@ int sangnom_cuda_submit(sn_ctx* ctx, const sn_plane_job* jobs, int njobs, sn_tic
     return rc;
 }
 
-int sangnom_cuda_wait(sn_ctx* ctx, sn_ticket ticket)
+static int wait_impl(sn_ctx* ctx, sn_ticket ticket)
 {
     if (!ctx) return SN_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1003,7 +1005,7 @@ int sangnom_cuda_wait(sn_ctx* ctx, sn_ticket ticket)
     return drain_through(ctx, ticket);
 }
 
-int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs)
+static int process_planes_impl(sn_ctx* ctx, const sn_plane_job* jobs, int njobs)
 {
     if (!ctx) return SN_ERR_INVALID;
     if (njobs < 0 || (njobs > 0 && !jobs)) return ctx->fail(SN_ERR_INVALID, "bad job list");
@@ -1014,5 +1016,21 @@ int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs
     if (rc == SN_OK) rc = drain_through(ctx, t);
     return rc;
 }
+
+
+// The C boundary does not let C++ exceptions through: allocation failures inside the library become SN_ERR_NOMEM.
+#define SN_NOTHROW(ctx, call)                                                                   \
+    try { return (call); }                                                                      \
+    catch (const std::bad_alloc&) { if (ctx) (ctx)->error = "out of host memory"; return SN_ERR_NOMEM; } \
+    catch (const std::exception& ex) { if (ctx) (ctx)->error = ex.what(); return SN_ERR_INVALID; } \
+    catch (...) { if (ctx) (ctx)->error = "unknown C++ exception"; return SN_ERR_INVALID; }
+
+int sangnom_cuda_process_planes_device(sn_ctx* ctx, const sn_plane_job* jobs, int njobs, void* cuda_stream)
+{
+    SN_NOTHROW(ctx, process_planes_device_impl(ctx, jobs, njobs, cuda_stream))
+}
+int sangnom_cuda_submit(sn_ctx* ctx, const sn_plane_job* jobs, int njobs, sn_ticket* ticket) { SN_NOTHROW(ctx, submit_impl(ctx, jobs, njobs, ticket)) }
+int sangnom_cuda_wait(sn_ctx* ctx, sn_ticket ticket) { SN_NOTHROW(ctx, wait_impl(ctx, ticket)) }
+int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs) { SN_NOTHROW(ctx, process_planes_impl(ctx, jobs, njobs)) }
 
 }  // extern "C"

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -159,7 +160,7 @@ int sangnom_cuda_chain_get_stats(sn_chain* ch, sn_chain_stats* out)
     return SN_OK;
 }
 
-int sangnom_cuda_chain_process(sn_chain* ch, const sn_chain_job* jobs, int njobs)
+static int chain_process_impl(sn_chain* ch, const sn_chain_job* jobs, int njobs)
 {
     if (!ch) return SN_ERR_INVALID;
     if (njobs < 0 || (njobs > 0 && !jobs)) return ch->fail(SN_ERR_INVALID, "bad job list");
@@ -324,6 +325,13 @@ int sangnom_cuda_chain_process(sn_chain* ch, const sn_chain_job* jobs, int njobs
         ch->stats.pass_kernel_launches = a.kernel_launches + b.kernel_launches;
     }
     return status;
+}
+
+int sangnom_cuda_chain_process(sn_chain* ch, const sn_chain_job* jobs, int njobs)
+{
+    try { return chain_process_impl(ch, jobs, njobs); }
+    catch (const std::bad_alloc&) { if (ch) ch->error = "out of host memory"; return SN_ERR_NOMEM; }
+    catch (...) { if (ch) ch->error = "C++ exception"; return SN_ERR_INVALID; }
 }
 
 int sangnom_cuda_turn_planes_device(int sample_type, int kind, const sn_turn_plane* planes, int nplanes, void* cuda_stream)
