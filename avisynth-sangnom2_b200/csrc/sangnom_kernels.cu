@@ -74,7 +74,11 @@ cudaError_t launch_u8_variant(const PlaneTask* tasks, int ntasks, LaunchGeometry
     const size_t smem = u8k::smem_bytes(seg);
     cudaError_t e = ensure_smem(kernel, smem, configured);
     if (e != cudaSuccess) return e;
-    return launch_clustered(kernel, ntasks * G, seg / u8k::kCols, smem, G, stream, tasks, g, seg);
+    // single-block planes get spare threads up to a whole number of warps plus one warp (at most 256): the kernel parks
+    // them behind the last pixel thread so that state-only threads start on a warp boundary (sangnom_u8.cuh)
+    const int T = seg / u8k::kCols;
+    const int threads = G == 1 ? std::min(256, ((T + 31) & ~31) + 32) : T;
+    return launch_clustered(kernel, ntasks * G, std::max(threads, T), smem, G, stream, tasks, g, seg);
 }
 
 // 8-bit: 8 columns per thread, at most 2048 columns per block.

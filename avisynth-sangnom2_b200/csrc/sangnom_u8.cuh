@@ -245,7 +245,7 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     const unsigned crank = kClustered ? cl::rank() : 0u;
     const int S = g.S;
     const uint32_t keymask = g.key_mask;                            // 0x0FF00FF0, kept in a register so (sum & mask) | rank is one LOP3
-    const int tid = (int)threadIdx.x, T = seg_cols / kCols;
+    const int T = seg_cols / kCols;                                 // working threads of the block
     uint2* const Lbase = reinterpret_cast<uint2*>(smem_raw);
     const int rstride = ring_stride(seg_cols);
     uint8_t* const ring = smem_raw + ((l_bytes(seg_cols) + 15) & ~(size_t)15);
@@ -262,8 +262,19 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     const PlaneTask& t = *reinterpret_cast<const PlaneTask*>(mbar + kRing);
 
     const int W = t.width, n = t.kept_rows, R = t.sweep_rows;
-    const int lx = tid * kCols;                                     // column inside the segment
     const int seg_x0 = (int)crank * seg_cols;
+    // Thread -> column map. A plane narrower than the pool (subsampled chroma in the luma-wide pool) ends its pixel
+    // threads inside a warp; that warp would carry pixel lanes AND state-only lanes (hand-over loads and stores), run
+    // both paths one after the other and be the slowest warp of the block, the one every row barrier waits for. The
+    // launch therefore brings spare threads, and `shift` of them are parked right behind the last pixel thread so
+    // that the state-only threads start on a warp boundary. Spare threads leave at once.
+    const int hw = (int)threadIdx.x;
+    const int Tpx = (min(max(W - seg_x0, 0), seg_cols) + kCols - 1) / kCols;       // threads of this segment that carry pixels
+    int shift = (!kClustered && Tpx > 0 && Tpx < T && (Tpx & 31) != 0) ? 32 - (Tpx & 31) : 0;
+    if (T + shift > (int)blockDim.x) shift = 0;
+    const bool spare = (hw >= Tpx && hw < Tpx + shift) || hw - shift >= T;
+    const int tid = hw < Tpx ? hw : hw - shift;
+    const int lx = tid * kCols;                                     // column inside the segment
     const int x0 = seg_x0 + lx;                                     // pool column
     const bool plane_first = x0 == 0, plane_last = x0 + kCols == S;
     const bool seg_first = tid == 0, seg_last = tid == T - 1;
@@ -274,6 +285,25 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     const int npix = min(max(W - x0, 0), kCols);
     const bool edge = npix > 0 && (x0 == 0 || x0 + 11 > W - 1);
     const bool vec_out = ((reinterpret_cast<uintptr_t>(t.plane) | (uintptr_t)t.pitch) & 7) == 0 && npix == kCols;   // aligned 8-byte stores
+
+    // Warp-uniform facts (every lane votes, spare lanes neutrally): do all lanes carry 8 pixel columns, and does any
+    // lane export to region A of the next pass?
+    const bool mine_a = t.out.a != nullptr && x0 >= t.out.a_x0;
+#ifdef SN_HOST_EMULATION
+    // the emulation has no warps: evaluate the predicates for the 32 threads this one would share a warp with
+    bool warp_full = true, warp_a = false;
+    for (int l = hw & ~31; l < (hw & ~31) + 32; ++l) {
+        if ((l >= Tpx && l < Tpx + shift) || l - shift >= T) continue;          // spare
+        const int xl = seg_x0 + (l < Tpx ? l : l - shift) * kCols;
+        warp_full = warp_full && min(max(W - xl, 0), kCols) == kCols;
+        warp_a = warp_a || (t.out.a != nullptr && xl >= t.out.a_x0);
+    }
+    if (spare) { emul::bar->arrive_and_drop(); return; }
+#else
+    const bool warp_full = __all_sync(0xFFFFFFFFu, spare || npix == kCols);
+    const bool warp_a = __any_sync(0xFFFFFFFFu, !spare && mine_a);
+    if (spare) return;
+#endif
 
     // ---- staging of kept rows: positions [lo, hi) of every kept row go to ring offset (position - seg_x0 + 16) ----
     const int lo = max(seg_x0 - kRingPad, 0), hi = min(seg_x0 + seg_cols + kRingPad, wpad);
@@ -398,13 +428,6 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     }
     // Threads without (all) pixel columns read the cost state the previous pass handed over. Those loads would open
     // every row and stall it for a DRAM round trip, so they run one row ahead: sp holds pool row r+1 at the top of row r.
-#ifdef SN_HOST_EMULATION
-    // the emulation has no warps: evaluate the predicate for the 32 threads this one would share a warp with
-    bool warp_full = true;
-    for (int l = tid & ~31; l < min((tid & ~31) + 32, T); ++l) warp_full = warp_full && min(max(W - (seg_x0 + l * kCols), 0), kCols) == kCols;
-#else
-    const bool warp_full = __all_sync(0xFFFFFFFFu, npix == kCols);
-#endif
     uint32_t sp[kNumCost][2];
     if (!warp_full) stale_costs(2, sp);
     // all blocks of a cluster run before the first DSMEM store
@@ -568,13 +591,6 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     int ex_b0 = 1, ex_b1 = 0, ex_a1 = 0;
     if (exporting) {
         if (t.out.b != nullptr) { ex_b0 = t.out.b_r0; ex_b1 = t.out.b_r1; }
-        const bool mine_a = t.out.a != nullptr && x0 >= t.out.a_x0;
-#ifdef SN_HOST_EMULATION
-        bool warp_a = false;
-        for (int l = tid & ~31; l < min((tid & ~31) + 32, T); ++l) warp_a = warp_a || (t.out.a != nullptr && seg_x0 + l * kCols >= t.out.a_x0);
-#else
-        const bool warp_a = __any_sync(0xFFFFFFFFu, mine_a);
-#endif
         if (warp_a) ex_a1 = t.out.a_rows;
     }
     auto export_row = [&](int r, StateRow& out) -> bool {

@@ -55,7 +55,8 @@ int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long lo
         const int cols = sample_bytes == 1 ? sn::u8k::kCols : sn::wide::kCols;
         if (S % (int)(G * cols) != 0) return -1;
         const int seg = S / (int)G;
-        const unsigned threads = (unsigned)(seg / cols);
+        unsigned threads = (unsigned)(seg / cols);
+        if (sample_bytes == 1 && G == 1) threads = std::max(threads, std::min(256u, ((threads + 31u) & ~31u) + 32u));      // spare threads, like the launcher
         // one block per plane runs the unclustered instantiation, like the launcher (it alone has the helper-lane path)
         if (sample_bytes == 1 && saturate && G == 1)
             emul::run_cluster(0, G, threads, sn::u8k::smem_bytes(seg), [&] { sn::u8k::sangnom_u8_row_sweep<1024, 1, false, true>(&t, g, seg); });
