@@ -434,7 +434,9 @@ int launch_passes(sn_ctx* ctx, const std::vector<std::vector<sn::PlaneTask>>& by
     size_t pos = 0;
     for (auto& v : by_pass) {
         if (v.empty()) continue;
-        SN_CUDA(ctx, sn::launch_plane_tasks(ctx->sample_bytes, dev_tasks + pos, (int)v.size(), sn::make_geometry(ctx->S, ctx->Hb, ctx->saturate), stream));
+        bool narrow = false;                 // any plane of this launch narrower than the pool by a thread's 8 columns or more
+        for (const sn::PlaneTask& t : v) narrow = narrow || t.width + 8 <= ctx->S;
+        SN_CUDA(ctx, sn::launch_plane_tasks(ctx->sample_bytes, dev_tasks + pos, (int)v.size(), sn::make_geometry(ctx->S, ctx->Hb, ctx->saturate, narrow), stream));
         ctx->stats.kernel_launches += 1;
         ctx->stats.planes_processed += v.size();
         pos += v.size();

@@ -65,20 +65,20 @@ int cluster_split(int S, int seg_max)
     return G;
 }
 
-// One instantiation per (split over a cluster?, arithmetic flavour); shared-memory opt-in remembered per device.
-template <bool kClustered, bool kSat>
+// One instantiation per (split over a cluster?, arithmetic flavour, spare threads?); shared-memory opt-in remembered per device.
+template <bool kClustered, bool kSat, bool kSpare>
 cudaError_t launch_u8_variant(const PlaneTask* tasks, int ntasks, LaunchGeometry g, int G, int seg, cudaStream_t stream)
 {
     static size_t configured[64] = {};
-    auto kernel = u8k::sangnom_u8_row_sweep<256, 2, kClustered, kSat>;
+    auto kernel = u8k::sangnom_u8_row_sweep<256, 2, kClustered, kSat, kSpare>;
     const size_t smem = u8k::smem_bytes(seg);
     cudaError_t e = ensure_smem(kernel, smem, configured);
     if (e != cudaSuccess) return e;
-    // single-block planes get spare threads up to a whole number of warps plus one warp (at most 256): the kernel parks
-    // them behind the last pixel thread so that state-only threads start on a warp boundary (sangnom_u8.cuh)
+    // kSpare: spare threads up to a whole number of warps plus one warp (at most 256); the kernel leaves the first few
+    // idle so that the last pixel thread ends a warp and the state-only threads start the next one (sangnom_u8.cuh)
     const int T = seg / u8k::kCols;
-    const int threads = G == 1 ? std::min(256, ((T + 31) & ~31) + 32) : T;
-    return launch_clustered(kernel, ntasks * G, std::max(threads, T), smem, G, stream, tasks, g, seg);
+    const int threads = kSpare ? std::max(T, std::min(256, ((T + 31) & ~31) + 32)) : T;
+    return launch_clustered(kernel, ntasks * G, threads, smem, G, stream, tasks, g, seg);
 }
 
 // 8-bit: 8 columns per thread, at most 2048 columns per block.
@@ -88,8 +88,12 @@ cudaError_t launch_u8(const PlaneTask* tasks, int ntasks, LaunchGeometry g, cuda
     const int G = cluster_split(g.S, seg_max);
     const int seg = g.S / G;
     if (seg > 2048 || seg % u8k::kCols != 0) return cudaErrorInvalidValue;
-    if (G == 1) return g.saturate ? launch_u8_variant<false, true>(tasks, ntasks, g, G, seg, stream) : launch_u8_variant<false, false>(tasks, ntasks, g, G, seg, stream);
-    return g.saturate ? launch_u8_variant<true, true>(tasks, ntasks, g, G, seg, stream) : launch_u8_variant<true, false>(tasks, ntasks, g, G, seg, stream);
+    if (G == 1) {
+        if (g.narrow && seg / u8k::kCols < 256)
+            return g.saturate ? launch_u8_variant<false, true, true>(tasks, ntasks, g, G, seg, stream) : launch_u8_variant<false, false, true>(tasks, ntasks, g, G, seg, stream);
+        return g.saturate ? launch_u8_variant<false, true, false>(tasks, ntasks, g, G, seg, stream) : launch_u8_variant<false, false, false>(tasks, ntasks, g, G, seg, stream);
+    }
+    return g.saturate ? launch_u8_variant<true, true, false>(tasks, ntasks, g, G, seg, stream) : launch_u8_variant<true, false, false>(tasks, ntasks, g, G, seg, stream);
 }
 
 template <typename T, bool kClustered, bool kSat>

@@ -45,8 +45,13 @@ struct LaunchGeometry {
     unsigned key_mask;      // 0x0FF00FF0 (8-bit kernel): passed as data so that it lives in a register, which lets
                             // (sum & mask) | rank compile to one LOP3; make_geometry() fills it
     int saturate;           // 0: opt=0 arithmetic (narrowing wraps); 1: the SSE2 path's (narrowing saturates) - selects the kernel flavour
+    int narrow;             // 1: some plane of the launch is narrower than the pool (subsampled chroma): the 8-bit launcher
+                            // brings spare threads and the kernel variant that realigns its warps to the picture edge
 };
-inline LaunchGeometry make_geometry(int S, int Hb, bool saturate = false) { return LaunchGeometry{ S, Hb, 0x0FF00FF0u, saturate ? 1 : 0 }; }
+inline LaunchGeometry make_geometry(int S, int Hb, bool saturate = false, bool narrow = false)
+{
+    return LaunchGeometry{ S, Hb, 0x0FF00FF0u, saturate ? 1 : 0, narrow ? 1 : 0 };
+}
 
 // Widest pool each sample type can run (columns per thread x max threads per block).
 int max_pool_width(int sample_bytes);

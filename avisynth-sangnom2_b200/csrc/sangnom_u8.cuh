@@ -235,7 +235,9 @@ inline size_t smem_bytes(int seg_cols)
            kRing * sizeof(stage::Mbar) + ((sizeof(PlaneTask) + 15) & ~(size_t)15);
 }
 
-template <int kMaxThreads, int kMinBlocks, bool kClustered, bool kSat = false>
+// kSpare: the launch brings spare threads for planes narrower than the pool (see the thread -> column map below); planes
+// as wide as the pool are launched without (kSpare = false: threadIdx.x is the working thread index, nothing else).
+template <int kMaxThreads, int kMinBlocks, bool kClustered, bool kSat = false, bool kSpare = false>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
 sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int seg_cols)
 {
@@ -266,14 +268,23 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     // Thread -> column map. A plane narrower than the pool (subsampled chroma in the luma-wide pool) ends its pixel
     // threads inside a warp; that warp would carry pixel lanes AND state-only lanes (hand-over loads and stores), run
     // both paths one after the other and be the slowest warp of the block, the one every row barrier waits for. The
-    // launch therefore brings spare threads, and `shift` of them are parked right behind the last pixel thread so
-    // that the state-only threads start on a warp boundary. Spare threads leave at once.
+    // launch therefore brings spare threads, and the first `shift` threads of the block are left idle so that the
+    // last pixel thread ends a warp and the state-only threads start the next one. Spare threads leave at once.
     const int hw = (int)threadIdx.x;
     const int Tpx = (min(max(W - seg_x0, 0), seg_cols) + kCols - 1) / kCols;       // threads of this segment that carry pixels
-    int shift = (!kClustered && Tpx > 0 && Tpx < T && (Tpx & 31) != 0) ? 32 - (Tpx & 31) : 0;
+    int shift = (kSpare && !kClustered && Tpx > 0 && Tpx < T && (Tpx & 31) != 0) ? 32 - (Tpx & 31) : 0;
     if (T + shift > (int)blockDim.x) shift = 0;
-    const bool spare = (hw >= Tpx && hw < Tpx + shift) || hw - shift >= T;
-    const int tid = hw < Tpx ? hw : hw - shift;
+    const int tid = kSpare ? hw - shift : hw;                       // working thread index (block-uniform offset)
+    if (kSpare && (tid < 0 || tid >= T)) {                          // spare thread: nothing to do, not even the barriers
+#ifdef SN_HOST_EMULATION
+        emul::bar->arrive_and_drop();
+#endif
+        return;
+    }
+    // (spare lanes have exited: the warp votes below may still name them in their mask)
+#ifdef SN_HOST_EMULATION
+    const int wfirst = max((hw & ~31) - shift, 0), wlast = min((hw & ~31) + 31 - shift, T - 1);       // working thread range of my "warp"
+#endif
     const int lx = tid * kCols;                                     // column inside the segment
     const int x0 = seg_x0 + lx;                                     // pool column
     const bool plane_first = x0 == 0, plane_last = x0 + kCols == S;
@@ -286,24 +297,6 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     const bool edge = npix > 0 && (x0 == 0 || x0 + 11 > W - 1);
     const bool vec_out = ((reinterpret_cast<uintptr_t>(t.plane) | (uintptr_t)t.pitch) & 7) == 0 && npix == kCols;   // aligned 8-byte stores
 
-    // Warp-uniform facts (every lane votes, spare lanes neutrally): do all lanes carry 8 pixel columns, and does any
-    // lane export to region A of the next pass?
-    const bool mine_a = t.out.a != nullptr && x0 >= t.out.a_x0;
-#ifdef SN_HOST_EMULATION
-    // the emulation has no warps: evaluate the predicates for the 32 threads this one would share a warp with
-    bool warp_full = true, warp_a = false;
-    for (int l = hw & ~31; l < (hw & ~31) + 32; ++l) {
-        if ((l >= Tpx && l < Tpx + shift) || l - shift >= T) continue;          // spare
-        const int xl = seg_x0 + (l < Tpx ? l : l - shift) * kCols;
-        warp_full = warp_full && min(max(W - xl, 0), kCols) == kCols;
-        warp_a = warp_a || (t.out.a != nullptr && xl >= t.out.a_x0);
-    }
-    if (spare) { emul::bar->arrive_and_drop(); return; }
-#else
-    const bool warp_full = __all_sync(0xFFFFFFFFu, spare || npix == kCols);
-    const bool warp_a = __any_sync(0xFFFFFFFFu, !spare && mine_a);
-    if (spare) return;
-#endif
 
     // ---- staging of kept rows: positions [lo, hi) of every kept row go to ring offset (position - seg_x0 + 16) ----
     const int lo = max(seg_x0 - kRingPad, 0), hi = min(seg_x0 + seg_cols + kRingPad, wpad);
@@ -428,13 +421,19 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     }
     // Threads without (all) pixel columns read the cost state the previous pass handed over. Those loads would open
     // every row and stall it for a DRAM round trip, so they run one row ahead: sp holds pool row r+1 at the top of row r.
+#ifdef SN_HOST_EMULATION
+    // the emulation has no warps: evaluate the predicate for the threads this one would share a warp with
+    bool warp_full = true;
+    for (int l = wfirst; l <= wlast; ++l) warp_full = warp_full && min(max(W - (seg_x0 + l * kCols), 0), kCols) == kCols;
+#else
+    const bool warp_full = __all_sync(0xFFFFFFFFu, npix == kCols);
+#endif
     uint32_t sp[kNumCost][2];
     if (!warp_full) stale_costs(2, sp);
     // all blocks of a cluster run before the first DSMEM store
     if constexpr (kClustered) cl::sync_all();
 
     const uint32_t tkey = (uint32_t)min(t.thr_i + 1, 4095) * 0x00100010u;    // (thr+1) << 4 in both lanes
-    const bool exporting = t.out.a != nullptr || t.out.b != nullptr;
 
     // One pool row. kFull: every thread of the warp owns 8 pixel columns (no stale-state or masking code on the hot
     // path). kPair: row r+1 is a pair row (r + 1 <= n - 1), i.e. its costs come from pixels.
@@ -584,15 +583,22 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
             }
         }
     };
-    // does any thread of my warp export pool row r? (warp-uniform, so the two variants of a row keep warps whole)
     // The rows my warp exports are two ranges known up front (region B: rows b_r0..b_r1, all columns; region A: rows
     // 1..a_rows for the warps that reach past a_x0), so the per-row question is two register compares; the task's
     // region description is read from shared memory only for rows that are exported.
     int ex_b0 = 1, ex_b1 = 0, ex_a1 = 0;
-    if (exporting) {
-        if (t.out.b != nullptr) { ex_b0 = t.out.b_r0; ex_b1 = t.out.b_r1; }
+    if (t.out.b != nullptr) { ex_b0 = t.out.b_r0; ex_b1 = t.out.b_r1; }
+    {
+        const bool mine_a = t.out.a != nullptr && x0 >= t.out.a_x0;
+#ifdef SN_HOST_EMULATION
+        bool warp_a = false;
+        for (int l = wfirst; l <= wlast; ++l) warp_a = warp_a || (t.out.a != nullptr && seg_x0 + l * kCols >= t.out.a_x0);
+#else
+        const bool warp_a = __any_sync(0xFFFFFFFFu, mine_a);
+#endif
         if (warp_a) ex_a1 = t.out.a_rows;
     }
+    // does my warp export pool row r? (warp-uniform, so the variants of a row keep warps whole)
     auto export_row = [&](int r, StateRow& out) -> bool {
         out = StateRow{ nullptr, 0 };
         if (!((r >= ex_b0 && r <= ex_b1) || r <= ex_a1)) return false;

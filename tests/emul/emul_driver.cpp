@@ -50,15 +50,21 @@ int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long lo
         t.thr_f = thresholds[q];
         t.thr_i = sample_bytes == 1 ? ((int)thresholds[q] & 0xFF) : ((int)thresholds[q] & 0xFFFF);
         t.in = geo[q].in; t.out = geo[q].out;
-        const sn::LaunchGeometry g = sn::make_geometry(S, Hb, saturate != 0);
+        const bool narrow = widths[q] + 8 <= S;
+        const sn::LaunchGeometry g = sn::make_geometry(S, Hb, saturate != 0, narrow);
         const unsigned G = (unsigned)cluster;
         const int cols = sample_bytes == 1 ? sn::u8k::kCols : sn::wide::kCols;
         if (S % (int)(G * cols) != 0) return -1;
         const int seg = S / (int)G;
         unsigned threads = (unsigned)(seg / cols);
-        if (sample_bytes == 1 && G == 1) threads = std::max(threads, std::min(256u, ((threads + 31u) & ~31u) + 32u));      // spare threads, like the launcher
+        const bool spare_threads = sample_bytes == 1 && G == 1 && narrow && threads < 256;
+        if (spare_threads) threads = std::max(threads, std::min(256u, ((threads + 31u) & ~31u) + 32u));      // like the launcher
         // one block per plane runs the unclustered instantiation, like the launcher (it alone has the helper-lane path)
-        if (sample_bytes == 1 && saturate && G == 1)
+        if (spare_threads && saturate)
+            emul::run_cluster(0, G, threads, sn::u8k::smem_bytes(seg), [&] { sn::u8k::sangnom_u8_row_sweep<1024, 1, false, true, true>(&t, g, seg); });
+        else if (spare_threads)
+            emul::run_cluster(0, G, threads, sn::u8k::smem_bytes(seg), [&] { sn::u8k::sangnom_u8_row_sweep<1024, 1, false, false, true>(&t, g, seg); });
+        else if (sample_bytes == 1 && saturate && G == 1)
             emul::run_cluster(0, G, threads, sn::u8k::smem_bytes(seg), [&] { sn::u8k::sangnom_u8_row_sweep<1024, 1, false, true>(&t, g, seg); });
         else if (sample_bytes == 1 && G == 1)
             emul::run_cluster(0, G, threads, sn::u8k::smem_bytes(seg), [&] { sn::u8k::sangnom_u8_row_sweep<1024, 1, false>(&t, g, seg); });
