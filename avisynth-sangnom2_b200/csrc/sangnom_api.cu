@@ -8,6 +8,10 @@
 #include "sangnom_cuda.h"
 #include "sangnom_kernels.h"
 #include "sangnom_plan.h"
+#include "host_copy_pool.h"
+
+using sn_host::CopyPool;
+using sn_host::RowCopy;
 
 #include <atomic>
 #include <condition_variable>
@@ -33,95 +37,6 @@
 namespace {
 
 thread_local std::string g_create_error;
-
-// Host-side row copies (packing pageable frames into pinned staging, unpacking finished planes, whole-plane copies of
-// planes that are not interpolated - the reference's BitBlt/memcpy, SangNom2.cpp:361-377) are memory-bound and a single
-// thread moves only a few GB/s, far less than the PCIe link behind it. They are collected per chunk and run by a
-// small pool of worker threads; the calling thread takes part.
-struct RowCopy { char* dst; const char* src; ptrdiff_t dst_pitch, src_pitch; size_t row_bytes; int rows; };
-
-class CopyPool {
-    std::vector<std::thread> workers_;
-    std::mutex mu_;
-    std::condition_variable wake_, done_;
-    const std::vector<RowCopy>* jobs_ = nullptr;
-    std::atomic<size_t> next_{ 0 };
-    size_t total_ = 0;
-    int active_ = 0;
-    uint64_t generation_ = 0;
-    bool stop_ = false;
-    static constexpr int kRowsPerPiece = 64;
-
-    static void copy_piece(const RowCopy& c, int r0, int r1)
-    {
-        for (int y = r0; y < r1; ++y) std::memcpy(c.dst + (ptrdiff_t)y * c.dst_pitch, c.src + (ptrdiff_t)y * c.src_pitch, c.row_bytes);
-    }
-    // pieces are numbered across all jobs: job j contributes ceil(rows / kRowsPerPiece) of them
-    void drain(const std::vector<RowCopy>& jobs, const std::vector<size_t>& first_piece)
-    {
-        for (;;) {
-            const size_t piece = next_.fetch_add(1, std::memory_order_relaxed);
-            if (piece >= total_) return;
-            const size_t j = (size_t)(std::upper_bound(first_piece.begin(), first_piece.end(), piece) - first_piece.begin()) - 1;
-            const int r0 = (int)(piece - first_piece[j]) * kRowsPerPiece;
-            copy_piece(jobs[j], r0, std::min(jobs[j].rows, r0 + kRowsPerPiece));
-        }
-    }
-    std::vector<size_t> first_piece_;
-    void worker()
-    {
-        uint64_t seen = 0;
-        for (;;) {
-            {
-                std::unique_lock<std::mutex> lk(mu_);
-                wake_.wait(lk, [&] { return stop_ || generation_ != seen; });
-                if (stop_) return;
-                seen = generation_;
-            }
-            drain(*jobs_, first_piece_);
-            {
-                std::lock_guard<std::mutex> lk(mu_);
-                if (--active_ == 0) done_.notify_all();
-            }
-        }
-    }
-public:
-    explicit CopyPool(int threads)
-    {
-        for (int i = 0; i < threads; ++i) workers_.emplace_back([this] { worker(); });
-    }
-    ~CopyPool()
-    {
-        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
-        wake_.notify_all();
-        for (auto& t : workers_) t.join();
-    }
-    // Runs every copy of `jobs`; returns when all are done. One caller at a time (the context lock is held).
-    void run(const std::vector<RowCopy>& jobs)
-    {
-        if (jobs.empty()) return;
-        first_piece_.assign(jobs.size() + 1, 0);
-        size_t bytes = 0;
-        for (size_t j = 0; j < jobs.size(); ++j) {
-            first_piece_[j + 1] = first_piece_[j] + (size_t)(jobs[j].rows + kRowsPerPiece - 1) / kRowsPerPiece;
-            bytes += jobs[j].row_bytes * (size_t)jobs[j].rows;
-        }
-        total_ = first_piece_.back();
-        first_piece_.pop_back();
-        next_.store(0, std::memory_order_relaxed);
-        if (workers_.empty() || bytes < (size_t)1 << 20) { drain(jobs, first_piece_); return; }     // small: not worth waking anyone
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            jobs_ = &jobs;
-            active_ = (int)workers_.size();
-            ++generation_;
-        }
-        wake_.notify_all();
-        drain(jobs, first_piece_);
-        std::unique_lock<std::mutex> lk(mu_);
-        done_.wait(lk, [&] { return active_ == 0; });
-    }
-};
 
 struct DevBuf {
     void* p = nullptr;

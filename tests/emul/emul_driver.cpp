@@ -4,6 +4,7 @@
 #include "cuda_emul.h"
 
 #include "sangnom_plan.h"
+#include "host_copy_pool.h"
 #include "sangnom_u8.cuh"
 #include "sangnom_wide.cuh"
 #include "sangnom_turn.cuh"
@@ -101,6 +102,36 @@ int emul_turn(int sample_bytes, int kind, const void* src, long long src_pitch, 
             else sn::turn::sangnom_turn_planes<4>(batch, 1, tiles, fr, fc);
         };
         emul::run_block((unsigned)b, sn::turn::kThreads, sn::turn::smem_bytes(sample_bytes), body);
+    }
+    return 0;
+}
+
+// The host copy pool of libsangnom_cuda on its own: `rounds` batches of random strided row copies (sizes from a few
+// bytes to several MB per batch, so that both the single-threaded short cut and the worker path run) against plain
+// memcpy. Returns 0, or the number of the first batch that differs.
+int emul_copy_pool_selftest(int threads, int rounds, unsigned seed)
+{
+    sn_host::CopyPool pool(threads > 0 ? threads - 1 : 0);
+    uint64_t state = seed * 2654435761u + 1;
+    auto rnd = [&](uint32_t n) { state = state * 6364136223846793005ULL + 1442695040888963407ULL; return (uint32_t)((state >> 33) % n); };
+    for (int round = 1; round <= rounds; ++round) {
+        const int njobs = 1 + (int)rnd(24);
+        std::vector<std::vector<char>> src((size_t)njobs), dst((size_t)njobs), ref((size_t)njobs);
+        std::vector<sn_host::RowCopy> jobs;
+        for (int j = 0; j < njobs; ++j) {
+            const size_t row = 1 + rnd(round % 3 == 0 ? 9000 : 300);
+            const int rows = 1 + (int)rnd(round % 3 == 0 ? 700 : 40);
+            const ptrdiff_t sp = (ptrdiff_t)(row + rnd(64)), dp = (ptrdiff_t)(row + rnd(64));
+            src[(size_t)j].resize((size_t)sp * rows);
+            dst[(size_t)j].assign((size_t)dp * rows, (char)0x5A);
+            ref[(size_t)j].assign((size_t)dp * rows, (char)0x5A);
+            for (char& c : src[(size_t)j]) c = (char)rnd(256);
+            for (int y = 0; y < rows; ++y) std::memcpy(ref[(size_t)j].data() + (size_t)y * dp, src[(size_t)j].data() + (size_t)y * sp, row);
+            jobs.push_back(sn_host::RowCopy{ dst[(size_t)j].data(), src[(size_t)j].data(), dp, sp, row, rows });
+        }
+        pool.run(jobs);
+        for (int j = 0; j < njobs; ++j)
+            if (dst[(size_t)j] != ref[(size_t)j]) return round;
     }
     return 0;
 }
