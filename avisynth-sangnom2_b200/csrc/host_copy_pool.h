@@ -10,6 +10,9 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace sn_host {
 
@@ -31,9 +34,39 @@ class CopyPool {
     bool stop_ = false;
     static constexpr int kRowsPerPiece = 64;
 
+    // One row. Rows of a frame are written once and not read again by this CPU soon (the staging buffer is read by the
+    // DMA engine, a finished frame by whoever consumes it later), so long rows go out with streaming stores: no
+    // read-for-ownership of the destination lines, a third less memory traffic on a copy that is bandwidth-bound.
+    static void copy_row(char* dst, const char* src, size_t n)
+    {
+#if defined(__SSE2__)
+        if (n >= 512) {
+            const size_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+            std::memcpy(dst, src, head);
+            dst += head; src += head; n -= head;
+            size_t i = 0;
+            for (; i + 64 <= n; i += 64) {
+                const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+                const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 16));
+                const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 32));
+                const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 48));
+                _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), a);
+                _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 16), b);
+                _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 32), c);
+                _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 48), d);
+            }
+            std::memcpy(dst + i, src + i, n - i);
+            return;
+        }
+#endif
+        std::memcpy(dst, src, n);
+    }
     static void copy_piece(const RowCopy& c, int r0, int r1)
     {
-        for (int y = r0; y < r1; ++y) std::memcpy(c.dst + (ptrdiff_t)y * c.dst_pitch, c.src + (ptrdiff_t)y * c.src_pitch, c.row_bytes);
+        for (int y = r0; y < r1; ++y) copy_row(c.dst + (ptrdiff_t)y * c.dst_pitch, c.src + (ptrdiff_t)y * c.src_pitch, c.row_bytes);
+#if defined(__SSE2__)
+        _mm_sfence();                           // streaming stores are visible before the piece counts as done
+#endif
     }
     // pieces are numbered across all jobs: job j contributes ceil(rows / kRowsPerPiece) of them
     void drain(const std::vector<RowCopy>& jobs, const std::vector<size_t>& first_piece)
