@@ -84,7 +84,7 @@ cudaError_t launch_u8_variant(const PlaneTask* tasks, int ntasks, LaunchGeometry
 // 8-bit: 8 columns per thread, at most 2048 columns per block.
 cudaError_t launch_u8(const PlaneTask* tasks, int ntasks, LaunchGeometry g, cudaStream_t stream)
 {
-    static const int seg_max = std::min(std::max(env_int("SANGNOM_U8_SEG", 2048), 256), 2048);     // tuning knob
+    const int seg_max = std::min(std::max(env_int("SANGNOM_U8_SEG", 2048), 256), 2048);     // tuning / test knob, read per launch: small values force cluster splits at small sizes
     const int G = cluster_split(g.S, seg_max);
     const int seg = g.S / G;
     if (seg > 2048 || seg % u8k::kCols != 0) return cudaErrorInvalidValue;
@@ -112,7 +112,7 @@ cudaError_t launch_wide_variant(const PlaneTask* tasks, int ntasks, LaunchGeomet
 template <typename T>
 cudaError_t launch_wide(const PlaneTask* tasks, int ntasks, LaunchGeometry g, cudaStream_t stream)
 {
-    static const int seg_max = std::min(std::max(env_int("SANGNOM_WIDE_SEG", 1024), 128), 1024);   // tuning knob
+    const int seg_max = std::min(std::max(env_int("SANGNOM_WIDE_SEG", 1024), 128), 1024);   // tuning / test knob, read per launch
     const int G = cluster_split(g.S, seg_max);
     const int seg = g.S / G;
     if (seg > 1024 || seg % wide::kCols != 0) return cudaErrorInvalidValue;

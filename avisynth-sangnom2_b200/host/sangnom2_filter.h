@@ -4,7 +4,7 @@
 // (/root/reference/src/SangNom2.h:40-67, SangNom2.cpp:275-330) but owns no scratch pool and no
 // CPU kernels: GetFrame is a thin host layer that batches frames into libsangnom_cuda
 // (include/sangnom_cuda.h). Uses only AviSynth+ API that exists with the same meaning in the real
-// avisynth.h, so it builds against the SDK header as well as against host/avs_stub/avisynth.h.
+// avisynth.h, so it builds against the SDK header as well as against the tests' stand-in tests/fakehost_src/avs_stub/avisynth.h.
 #pragma once
 
 #include <map>

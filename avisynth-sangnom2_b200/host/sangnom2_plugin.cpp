@@ -33,9 +33,10 @@ SangNom2::SangNom2(PClip _child, int order, int aa, int aac, int threads, bool d
     : GenericVideoFilter(_child), order_(order), dh_(dh), aaf_{ 0.0f, 0.0f, 0.0f }, process_plane_{ luma, chroma, chroma }
 {
     (void)threads;   // dummy parameter, as in the reference (README.md:40-41)
-    // opt is validated by the factory. There is one code path; opt=1 selects the ARITHMETIC of the reference's SSE2
-    // path (narrowing saturates, SangNom2_SSE2.cpp:449-517,761,807) for users who compare against an SSE2 build of the
-    // reference; opt=0 and opt=-1 give the opt=0 C++ arithmetic (narrowing wraps), the parity contract.
+    // opt is validated by the factory. There is one code path on the device; opt picks the ARITHMETIC flavour by the
+    // reference's own dispatch rule (:312): opt=1, or opt<0 on a host that reports SSE2, is the SSE2 path's arithmetic
+    // (narrowing saturates, SangNom2_SSE2.cpp:449-517,761,807); opt=0, or opt<0 without SSE2, is the C++ path's
+    // (narrowing wraps, :63-64,:152). So a script with default arguments gives what the stock reference gives.
     has_at_least_v8_ = env->FunctionExists("propShow");
     sample_bytes_ = vi.ComponentSize();
     plane_count_ = vi.NumComponents() < 3 ? vi.NumComponents() : 3;
@@ -63,7 +64,7 @@ SangNom2::SangNom2(PClip _child, int order, int aa, int aac, int threads, bool d
     // instance (bit-compatible with a sequential single-instance reference run where that is not frame-pure:
     // widths that are not a multiple of 32, luma=false with subsampled chroma). Frames then run one after another.
     if (env_int("SANGNOM_B200_PERSISTENT", 0, 0, 1)) cfg.flags |= SN_FLAG_PERSISTENT_POOL;
-    if (opt == 1) cfg.flags |= SN_FLAG_SATURATE;
+    if (opt == 1 || (opt < 0 && (env->GetCPUFlags() & CPUF_SSE2))) cfg.flags |= SN_FLAG_SATURATE;
     // SANGNOM_B200_PREFETCH=0: no speculative next batch (every child frame is requested only when it is needed)
     prefetch_ = env_int("SANGNOM_B200_PREFETCH", 1, 0, 1) != 0;
     if (sangnom_cuda_create(&cfg, &ctx_) != SN_OK)
@@ -197,7 +198,12 @@ PVideoFrame __stdcall SangNom2::GetFrame(int n, IScriptEnvironment* env)
         while (ready_.count(next)) ++next;
         if (next <= last && next - n <= batch_frames_) {
             const int count = window(next, batch_frames_);
-            if (count > 0) start_batch(next, count, env);
+            // Frame n is finished: a failure while fetching or submitting LATER frames must not fail this call. The
+            // prefetch is dropped and the error surfaces when one of those frames is actually requested.
+            if (count > 0) {
+                try { start_batch(next, count, env); }
+                catch (...) { pending_ = Pending{}; }
+            }
         }
     }
     // keep a bounded window of finished frames around the read position
@@ -250,7 +256,7 @@ AVSValue __cdecl Create_SangNom2(AVSValue args, void*, IScriptEnvironment* env)
 // :466-470). Observable result, reproduced here: the value the script passes as `opt` lands in
 // aac (default 0 when omitted, never range-checked); threads/dh/luma/chroma/opt come from
 // out-of-range subscripts and so take their defaults (0, false, true, true, -1), which also means
-// the opt checks can never fire for this function.
+// the opt checks can never fire for this function and that it always runs the host's default flavour (opt=-1).
 AVSValue __cdecl Create_SangNom(AVSValue args, void*, IScriptEnvironment* env)
 {
     PClip clip = args[0].AsClip();

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .fakehost import ClipFormat
+from .formats import ClipFormat
 
 
 def _max_code(fmt: ClipFormat):

@@ -26,7 +26,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "avisynth-sangnom2_b200")
-for _p in (ROOT, PKG):
+for _p in (ROOT, PKG, os.path.join(ROOT, "tests")):     # tests/: the fake AviSynth host both plugin legs are driven by
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
@@ -55,7 +55,7 @@ def workload_desc(name):
 
 def algorithmic_bytes_per_frame(name):
     """W*H*s per processed plane: kept field read once + interpolated rows written once."""
-    from pysangnom.fakehost import FORMATS
+    from pysangnom.formats import FORMATS
     fmtname, w, h, kw, _, _ = WORKLOADS[name]
     fmt = FORMATS[fmtname]
     total = 0
@@ -120,7 +120,8 @@ def reference_fps(workload, threads, seconds_budget, opt=-1, warm=1):
     disjoint frame ranges (what MT_MULTI_INSTANCE + Prefetch(threads) does in AviSynth+)."""
     from oracle import oracle as O
     from pysangnom.clips import make_frame
-    from pysangnom.fakehost import FORMATS, FakeHost
+    from pysangnom.formats import FORMATS
+    from fakehost import FakeHost
 
     plugin = O.reference_plugin_path()
     if plugin is None:
@@ -139,7 +140,7 @@ def reference_fps(workload, threads, seconds_budget, opt=-1, warm=1):
         filters.append(host.invoke("SangNom2", src, opt=opt, **kw))
         hosts.append(host)
 
-    from pysangnom import fakehost as fh
+    import fakehost as fh
     L = fh._load()
     err = C.create_string_buffer(256)
 
@@ -241,7 +242,7 @@ def run_ours(args):
     import torch.distributed as dist
     from pysangnom import cuda
     from pysangnom.clips import make_frame
-    from pysangnom.fakehost import FORMATS
+    from pysangnom.formats import FORMATS
     from pysangnom.shard import frame_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -485,8 +486,9 @@ def plugin_fps(wl, seconds):
     """The drop-in path itself: our AviSynth plugin pulled frame by frame through the fake host (PAGEABLE host frames,
     one filter instance, sequential GetFrame) - the same harness the reference arm is timed with."""
     from pysangnom.clips import make_frame
-    from pysangnom.fakehost import FORMATS, FakeHost
-    from pysangnom import fakehost as fh
+    from pysangnom.formats import FORMATS
+    from fakehost import FakeHost
+    import fakehost as fh
     fmtname, w, h, kw, _, _ = WORKLOADS[wl]
     fmt = FORMATS[fmtname]
     ours = os.path.join(PKG, "libsangnom2_b200.so")
@@ -524,7 +526,7 @@ def cpu_port_baseline(wl, seconds):
     """Fallback when oracle/_ref is absent: our C restatement, single thread."""
     from oracle import oracle as O
     from pysangnom.clips import make_frame
-    from pysangnom.fakehost import FORMATS
+    from pysangnom.formats import FORMATS
     fmtname, w, h, kw, _, _ = WORKLOADS[wl]
     fmt = FORMATS[fmtname]
     fr = make_frame(1, w, h, fmt, "noise", 0)

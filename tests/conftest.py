@@ -17,7 +17,8 @@ def pytest_configure(config):
 @pytest.fixture(scope="session", autouse=True)
 def _built():
     """Everything the tests load is built in-tree by __graft_entry__.build(); build on demand here."""
-    need = [os.path.join(PKG, n) for n in ("libsangnom_cuda.so", "libsangnom2_b200.so", "libfakeavs.so")]
+    need = [os.path.join(PKG, n) for n in ("libsangnom_cuda.so", "libsangnom2_b200.so")]
+    need.append(os.path.join(ROOT, "tests", "fakehost_src", "libfakeavs.so"))
     need.append(os.path.join(ROOT, "oracle", "liboracle.so"))
     if not all(os.path.exists(p) for p in need) and not os.environ.get("SANGNOM_SKIP_BUILD"):
         import __graft_entry__

@@ -1,4 +1,4 @@
-"""ctypes driver for the fake AviSynth host (host/fake_host.cpp -> libfakeavs.so).
+"""ctypes driver for the fake AviSynth host (tests/fakehost_src/fake_host.cpp -> tests/fakehost_src/libfakeavs.so).
 
 Test infrastructure: loads an AviSynth plugin (.so exporting AvisynthPluginInit3) the way a
 frameserver would, builds source clips from numpy planes, calls the registered script functions
@@ -9,56 +9,20 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from dataclasses import dataclass
 
 import numpy as np
 
-_PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-FAKEHOST_LIB = os.path.join(_PKG_DIR, "libfakeavs.so")
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG = os.path.join(os.path.dirname(_HERE), "avisynth-sangnom2_b200")
+if _PKG not in sys.path:
+    sys.path.insert(0, _PKG)
+FAKEHOST_LIB = os.path.join(_HERE, "fakehost_src", "libfakeavs.so")
 CPUF_SSE2 = 0x20
 CACHE_GET_MTMODE = 509
 MT_NICE_FILTER, MT_MULTI_INSTANCE, MT_SERIALIZED = 1, 2, 3
-
-
-@dataclass(frozen=True)
-class ClipFormat:
-    """Planar format: components 1 (Y), 3 (YUV) or 4 (YUVA); log2 chroma subsampling; bit depth."""
-    components: int = 3
-    sub_w: int = 1
-    sub_h: int = 1
-    bits: int = 8
-    rgb: bool = False
-    planar: bool = True
-
-    @property
-    def dtype(self):
-        return np.uint8 if self.bits <= 8 else (np.uint16 if self.bits <= 16 else np.float32)
-
-    @property
-    def sample_bytes(self):
-        return np.dtype(self.dtype).itemsize
-
-    def plane_shape(self, width, height, plane):
-        if plane in (1, 2):
-            return (height >> self.sub_h, width >> self.sub_w)
-        return (height, width)
-
-
-# name -> ClipFormat, the spellings BASELINE.json uses
-FORMATS = {
-    "Y8": ClipFormat(1, 0, 0, 8), "Y10": ClipFormat(1, 0, 0, 10), "Y12": ClipFormat(1, 0, 0, 12),
-    "Y16": ClipFormat(1, 0, 0, 16), "Y32": ClipFormat(1, 0, 0, 32),
-    "YV12": ClipFormat(3, 1, 1, 8), "YUV420P8": ClipFormat(3, 1, 1, 8), "YUV420P10": ClipFormat(3, 1, 1, 10),
-    "YUV420P16": ClipFormat(3, 1, 1, 16), "YUV420PS": ClipFormat(3, 1, 1, 32),
-    "YV16": ClipFormat(3, 1, 0, 8), "YUV422P8": ClipFormat(3, 1, 0, 8), "YUV422P10": ClipFormat(3, 1, 0, 10),
-    "YUV422P16": ClipFormat(3, 1, 0, 16), "YUV422PS": ClipFormat(3, 1, 0, 32),
-    "YV24": ClipFormat(3, 0, 0, 8), "YUV444P8": ClipFormat(3, 0, 0, 8), "YUV444P10": ClipFormat(3, 0, 0, 10),
-    "YUV444P16": ClipFormat(3, 0, 0, 16), "YUV444PS": ClipFormat(3, 0, 0, 32),
-    "YV411": ClipFormat(3, 2, 0, 8),
-    "YUVA420P8": ClipFormat(4, 1, 1, 8), "YUVA444P16": ClipFormat(4, 0, 0, 16), "YUVA444PS": ClipFormat(4, 0, 0, 32),
-    "RGB24": ClipFormat(3, 0, 0, 8, rgb=True, planar=False), "RGBP8": ClipFormat(3, 0, 0, 8, rgb=True, planar=True),
-    "YUY2": ClipFormat(3, 1, 0, 8, rgb=False, planar=False),
-}
+from pysangnom.formats import FORMATS, ClipFormat  # noqa: E402,F401
 
 
 class AvisynthError(RuntimeError):
@@ -73,7 +37,7 @@ def _load():
     if _lib is not None:
         return _lib
     if not os.path.exists(FAKEHOST_LIB):
-        raise FileNotFoundError(f"{FAKEHOST_LIB} missing - run __graft_entry__.build() or make -C avisynth-sangnom2_b200")
+        raise FileNotFoundError(f"{FAKEHOST_LIB} missing - run __graft_entry__.build() or make -f tests/fakehost_src/Makefile")
     L = C.CDLL(FAKEHOST_LIB)
     vp, ci, cp = C.c_void_p, C.c_int, C.c_char_p
     L.fh_env_create.restype, L.fh_env_create.argtypes = vp, [ci, ci, ci]
@@ -89,6 +53,7 @@ def _load():
     L.fh_source_request_count.restype, L.fh_source_request_count.argtypes = ci, [vp]
     L.fh_source_request_at.restype, L.fh_source_request_at.argtypes = ci, [vp, ci]
     L.fh_source_clear_requests.restype, L.fh_source_clear_requests.argtypes = None, [vp]
+    L.fh_source_fail_at.restype, L.fh_source_fail_at.argtypes = None, [vp, ci]
     L.fh_clip_release.restype, L.fh_clip_release.argtypes = None, [vp]
     L.fh_invoke.restype = vp
     L.fh_invoke.argtypes = [vp, cp, vp, ci, C.POINTER(cp), C.POINTER(ci), cp, ci]
@@ -134,6 +99,10 @@ class Clip:
 
     def clear_requests(self):
         _load().fh_source_clear_requests(self.handle)
+
+    def fail_at(self, n):
+        """Fault injection: the source raises a script error when frame n is requested (-1: never)."""
+        _load().fh_source_fail_at(self.handle, int(n))
 
     def mt_mode(self):
         return _load().fh_clip_cache_hints(self.handle, CACHE_GET_MTMODE, 0)

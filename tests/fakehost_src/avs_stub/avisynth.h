@@ -6,10 +6,10 @@
 // that (a) the unmodified reference sources need in order to compile for the oracle build
 // (oracle/Makefile -> oracle/_ref/) and (b) our own plugin shim (host/sangnom2_plugin.cpp)
 // uses. The shim only calls methods that exist with the same meaning in the real header, so
-// it also builds against a real AviSynth+ SDK (CMake option SANGNOM_AVISYNTH_INCLUDE).
+// it also builds against a real AviSynth+ SDK (CMake: -DAVS_INCLUDE_DIR=<dir>; make: AVS_INC=<dir>).
 //
 // This is NOT a reimplementation of AviSynth: there is no script parser, no cache, no audio.
-// The matching fake host (host/fake_host.cpp) implements IScriptEnvironment just far enough
+// The matching fake host (../fake_host.cpp) implements IScriptEnvironment just far enough
 // to load a plugin through AvisynthPluginInit3, call a registered factory with an AVSValue
 // array and pull frames.
 //

@@ -113,15 +113,17 @@ public:
     std::mutex mu;
 
     bool log_requests = true;
+    int fail_at = -1;            // fault injection: GetFrame(fail_at) raises a script error
     // stored < num_frames: a long clip that repeats its `stored` frames (for throughput runs)
     SourceClip(const VideoInfo& v, int pm, int stored = 0) : vi(v), parity_mode(pm) {
         frames.resize((size_t)(stored > 0 ? stored : v.num_frames));
         for (auto& f : frames) f = PVideoFrame(new VideoFrame(vi, FRAME_ALIGN, false));
         log_requests = stored <= 0;
     }
-    PVideoFrame __stdcall GetFrame(int n, IScriptEnvironment*) override {
+    PVideoFrame __stdcall GetFrame(int n, IScriptEnvironment* env) override {
         std::lock_guard<std::mutex> lk(mu);
         if (log_requests) requests.push_back(n);
+        if (n == fail_at) env->ThrowError("FakeSource: injected failure at frame %d", n);
         n = std::max(0, std::min(n, vi.num_frames - 1));
         return frames[(size_t)n % frames.size()];
     }
@@ -235,6 +237,7 @@ int fh_source_set_prop(void* clip, int n, const char* key, long long value) {
 int fh_source_request_count(void* clip) { return (int)static_cast<ClipHandle*>(clip)->source->requests.size(); }
 int fh_source_request_at(void* clip, int i) { return static_cast<ClipHandle*>(clip)->source->requests[(size_t)i]; }
 void fh_source_clear_requests(void* clip) { static_cast<ClipHandle*>(clip)->source->requests.clear(); }
+void fh_source_fail_at(void* clip, int n) { static_cast<ClipHandle*>(clip)->source->fail_at = n; }
 
 void fh_clip_release(void* clip) { delete static_cast<ClipHandle*>(clip); }
 

@@ -19,7 +19,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "avisynth-sangnom2_b200"), os.path.join
 
 from helpers import CASES, case_frames, parity_of  # noqa: E402
 from oracle import oracle as O  # noqa: E402
-from pysangnom.fakehost import FakeHost  # noqa: E402
+from fakehost import FakeHost  # noqa: E402
 
 
 def sha(a):

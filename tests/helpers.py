@@ -3,7 +3,7 @@ import numpy as np
 
 from oracle import oracle as O
 from pysangnom.clips import make_frame
-from pysangnom.fakehost import FORMATS
+from pysangnom.formats import FORMATS
 
 # (name, format, width, height, script arguments, content kind, frames)
 # The BASELINE.json configs at sizes the CPU oracle finishes in seconds, plus the edge cases the

@@ -9,7 +9,7 @@ import pytest
 from helpers import assert_planes_equal
 from oracle import oracle as O
 from pysangnom.clips import make_frame
-from pysangnom.fakehost import FORMATS
+from pysangnom.formats import FORMATS
 
 pytestmark = pytest.mark.gpu
 

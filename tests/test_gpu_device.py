@@ -8,7 +8,7 @@ import torch
 from helpers import assert_planes_equal, parity_of
 from oracle import oracle as O
 from pysangnom.clips import make_frame
-from pysangnom.fakehost import FORMATS
+from pysangnom.formats import FORMATS
 
 pytestmark = pytest.mark.gpu
 
@@ -120,14 +120,65 @@ def test_full_size_properties(cuda, fmtname, w, h, kw):
             assert np.array_equal(mid, exp)
 
 
-@pytest.mark.parametrize("fmtname,w,h,kw", [("Y8", 7680, 4320, dict(order=2, aa=48)), ("YUV420P8", 1920, 1080, dict(order=0, aa=48, aac=48)),
-                                            ("Y16", 8192, 256, dict(order=1, aa=48)), ("Y32", 8192, 128, dict(order=1, aa=48))],
-                         ids=["cfg5a_8k_y8", "cfg2_1080p", "widest_u16", "widest_f32"])
-def test_full_size_against_oracle(cuda, fmtname, w, h, kw):
-    """One frame at BASELINE.json's largest sizes and at the widest planes the kernels accept (8-block clusters),
-    bit-exact against the oracle."""
+# Every BASELINE.json configuration at its full size (plus the widest planes the kernels accept), one or two frames,
+# bit-exact against the oracle through BOTH entries. The rows after cfg2 are the launches whose planes are split over
+# a thread-block cluster AND are narrower than the pool (subsampled chroma: the hand-over regions cross segment
+# boundaries), the pad-column case of the AA chain's second stage (S = 2176), and the widest planes.
+FULL_ORACLE = [
+    ("cfg2_1080p_420p8", "YUV420P8", 1920, 1080, dict(order=0, aa=48, aac=48), 2),
+    ("cfg3_stage1_444p16_dh", "YUV444P16", 1920, 1080, dict(dh=True, aa=48), 1),
+    ("cfg3_stage2_444p16_dh_T", "YUV444P16", 2160, 1920, dict(dh=True, aa=48), 1),
+    ("cfg4_2160p_420ps", "YUV420PS", 3840, 2160, dict(order=2, aa=48, aac=24), 1),
+    ("cfg5a_8k_y8", "Y8", 7680, 4320, dict(order=2, aa=48), 1),
+    ("cfg5b_2160p_420p10", "YUV420P10", 3840, 2160, dict(order=1, aa=48, aac=48), 1),
+    ("uhd_420p8_cluster_chroma", "YUV420P8", 3840, 2160, dict(order=0, aa=48, aac=48), 2),
+    ("uhd_422p8_cluster_chroma", "YUV422P8", 3840, 1080, dict(order=2, aa=48, aac=30), 1),
+    ("uhd_411_cluster_chroma", "YV411", 4096, 540, dict(order=1, aa=48, aac=48), 1),
+    ("widest_u16", "Y16", 8192, 256, dict(order=1, aa=48), 1),
+    ("widest_f32", "Y32", 8192, 128, dict(order=1, aa=48), 1),
+    ("u16_420_odd_segments", "YUV420P16", 2080, 540, dict(order=0, aa=48, aac=48), 2),
+]
+
+
+def device_frames_any(cuda, fmt, w, h, frames, kw):
+    """Device entry for any script arguments: dh (separated rows in, double-height plane out), disabled planes."""
+    sb = fmt.sample_bytes
+    dh = kw.get("dh", False)
+    order, aa, aac = kw.get("order", 1), kw.get("aa", 48), kw.get("aac", 0)
+    keep, jobs = [], []
+    with cuda.Context(sb, w, h * 2 if dh else h) as ctx:
+        for k, planes in enumerate(frames):
+            off = cuda.resolve_offset(order, parity_of(k))
+            for p, a in enumerate(planes[:3]):
+                enabled = dh or (kw.get("luma", True) if p == 0 else kw.get("chroma", True))
+                thr = cuda.threshold(aa if p == 0 else aac, fmt.bits, sb)
+                s, sp = to_dev(a)
+                d = torch.full((a.shape[0] * (2 if dh else 1), sp), 0xEE, dtype=torch.uint8, device="cuda")
+                mode = cuda.MODE_DH if dh else (cuda.MODE_FIELD if enabled else cuda.MODE_COPY)
+                jobs.append(cuda.make_job(s.data_ptr(), sp, d.data_ptr(), sp, a.shape[1], d.shape[0], off, mode, thr, p, k))
+                keep.append((d, a.shape[1], a.dtype, s))
+        ctx.process_jobs_device(jobs)
+        ctx.synchronize()
+    outs, i = [], 0
+    for planes in frames:
+        np_ = len(planes[:3])
+        outs.append([from_dev(keep[i + p][0], keep[i + p][1], keep[i + p][2]) for p in range(np_)])
+        i += np_
+    return outs
+
+
+@pytest.mark.parametrize("entry", ["device", "host"])
+@pytest.mark.parametrize("case", FULL_ORACLE, ids=[c[0] for c in FULL_ORACLE])
+def test_full_size_against_oracle(cuda, case, entry):
+    name, fmtname, w, h, kw, nframes = case
     fmt = FORMATS[fmtname]
-    fr = make_frame(23, w, h, fmt, "noise", 0)
-    got, _ = device_frames(cuda, fmt, w, h, [fr], mode="field", **kw)
-    exp = O.oracle_frame(fr, fmt.bits, parity=True, **kw)
-    assert_planes_equal(got[0], exp[:len(got[0])], f"{fmtname} {w}x{h}")
+    frames = [make_frame(23, w, h, fmt, "noise" if i == 0 else "edges", i) for i in range(nframes)]
+    args = dict(order=kw.get("order", 1), aa=kw.get("aa", 48), aac=kw.get("aac", 0), dh=kw.get("dh", False))
+    if entry == "device":
+        got = device_frames_any(cuda, fmt, w, h, frames, kw)
+    else:
+        with cuda.Context(fmt.sample_bytes, w, h * 2 if args["dh"] else h) as ctx:
+            got = ctx.process_frames(frames, fmt.bits, parities=[parity_of(i) for i in range(nframes)], **args)
+    for i, fr in enumerate(frames):
+        exp = O.oracle_frame(fr, fmt.bits, parity=parity_of(i), **args)
+        assert_planes_equal(got[i][:3], exp[:3], f"{name} {entry} frame {i}")

@@ -38,7 +38,7 @@ def test_host_path_matches_oracle(cuda, case):
 def test_overlapped_batches_submit_wait(cuda, pinned):
     """sangnom_cuda_submit / _wait: three batches in flight at once (more chunks than pipeline slots), waited out of
     submission order; every frame must equal the oracle and the synchronous call."""
-    from pysangnom.fakehost import FORMATS
+    from pysangnom.formats import FORMATS
     from pysangnom.clips import make_frame
     from oracle import oracle as O
     fmt, w, h = FORMATS["YUV420P8"], 352, 288
@@ -92,7 +92,7 @@ def test_persistent_pool_mode(cuda, case, entry):
     import torch
     from oracle import oracle as O
     from pysangnom.clips import make_frame
-    from pysangnom.fakehost import FORMATS
+    from pysangnom.formats import FORMATS
     name, fmtname, w, h, kw, nframes = case
     fmt = FORMATS[fmtname]
     dh = kw.get("dh", False)
@@ -136,7 +136,7 @@ def test_separated_fields_input(cuda):
     output frames as the woven input with order=0, half the upload."""
     from oracle import oracle as O
     from pysangnom.clips import make_frame
-    from pysangnom.fakehost import FORMATS
+    from pysangnom.formats import FORMATS
     fmt, w, h = FORMATS["YUV420P8"], 352, 288
     woven = [make_frame(12, w, h, fmt, "noise", i) for i in range(4)]
     fields = [[p[cuda.resolve_offset(0, parity_of(i))::2] for p in fr] for i, fr in enumerate(woven)]
@@ -160,7 +160,7 @@ def test_saturating_flavour(cuda, case):
     pinned to the compiled reference run with opt=1 in tests/test_oracle.py."""
     from oracle import oracle as O
     from pysangnom.clips import make_frame
-    from pysangnom.fakehost import FORMATS
+    from pysangnom.formats import FORMATS
     name, fmtname, w, h, kw = case
     fmt = FORMATS[fmtname]
     frames = [make_frame(500 + len(name), w, h, fmt, "noise", i) for i in range(2)]

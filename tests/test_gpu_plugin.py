@@ -11,7 +11,8 @@ from helpers import CASES, assert_planes_equal, case_frames, oracle_outputs, par
 from kat import KAT_IN, KATS
 from oracle import oracle as O
 from pysangnom.clips import make_frame
-from pysangnom.fakehost import FORMATS, MT_NICE_FILTER, FakeHost
+from pysangnom.formats import FORMATS
+from fakehost import MT_NICE_FILTER, FakeHost
 
 pytestmark = pytest.mark.gpu
 PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "avisynth-sangnom2_b200")
@@ -24,6 +25,9 @@ def sha(a):
 
 
 def run_plugin(plugin, fmt, w, h, frames, kw, func="SangNom2", fresh=False, **host_kw):
+    """Default host: one that reports no SSE2, i.e. opt=-1 resolves to the opt=0 C++ arithmetic (the parity contract)
+    on both plugins; tests of the SSE2 flavour pass cpu_flags=CPUF_SSE2."""
+    host_kw.setdefault("cpu_flags", 0)
     outs = []
     with FakeHost(**host_kw) as host:
         host.load_plugin(plugin)
@@ -93,13 +97,33 @@ def test_persistent_mode_equals_one_long_lived_reference_instance(monkeypatch, f
                                             ("YUV444P10", 200, 120, dict(dh=True, aa=30)), ("YUV420PS", 176, 144, dict(order=1, aa=48, aac=24))])
 def test_opt1_selects_the_sse2_arithmetic(fmtname, w, h, kw):
     """SangNom2(opt=1) on our plugin == the reference's SSE2 path (opt=1 on a host that reports SSE2)."""
-    from pysangnom.fakehost import CPUF_SSE2
+    from fakehost import CPUF_SSE2
     fmt = FORMATS[fmtname]
     frames = [make_frame(19, w, h, fmt, "noise", i) for i in range(3)]
     ref = run_plugin(O.reference_plugin_path(), fmt, w, h, frames, dict(opt=1, **kw), fresh=True, cpu_flags=CPUF_SSE2)
     got = run_plugin(OURS, fmt, w, h, frames, dict(opt=1, **kw), cpu_flags=CPUF_SSE2)
     for i in range(len(frames)):
         assert_planes_equal(got[i][:3], ref[i][:3], f"opt=1 {fmtname} {kw} frame {i}")
+
+
+@pytest.mark.skipif(O.reference_plugin_path() is None, reason="oracle/_ref not built")
+@pytest.mark.parametrize("func,kw", [("SangNom2", dict()), ("SangNom2", dict(order=0, aac=48)), ("SangNom", dict()), ("SangNom", dict(order=2, aa=64))])
+@pytest.mark.parametrize("fmtname", ["YV12", "YUV420P10", "YUV444P16", "YUV420PS"])
+def test_default_arguments_equal_the_stock_reference(func, kw, fmtname):
+    """A script that does not pass opt gets, on an SSE2 host (every x86-64 host), the reference's SSE2 arithmetic
+    (SangNom2.cpp:312: `opt < 0 && CPUF_SSE2`) - from our plugin too, including the legacy SangNom() entry, which can
+    never pass opt at all. Noise content, where the two flavours differ."""
+    from fakehost import CPUF_SSE2
+    fmt = FORMATS[fmtname]
+    w, h = 176, 144
+    frames = [make_frame(31, w, h, fmt, "noise", i) for i in range(3)]
+    ref = run_plugin(O.reference_plugin_path(), fmt, w, h, frames, kw, func=func, fresh=True, cpu_flags=CPUF_SSE2)
+    got = run_plugin(OURS, fmt, w, h, frames, kw, func=func, cpu_flags=CPUF_SSE2)
+    for i in range(len(frames)):
+        assert_planes_equal(got[i][:3], ref[i][:3], f"{func} {kw} {fmtname} default-opt frame {i}")
+    if fmt.sample_bytes == 1:
+        wrap = run_plugin(OURS, fmt, w, h, frames, kw, func=func, cpu_flags=0)
+        assert any(not np.array_equal(a, b) for fa, fb in zip(got, wrap) for a, b in zip(fa[:3], fb[:3])), "flavours should differ on noise"
 
 
 def test_legacy_semantics_without_reference():
@@ -120,7 +144,7 @@ def test_legacy_semantics_without_reference():
 def test_filter_object_properties():
     fmt = FORMATS["YUVA420P8"]
     w, h, n = 64, 32, 5
-    with FakeHost() as host:
+    with FakeHost(cpu_flags=0) as host:
         host.load_plugin(OURS)
         src = host.source(w, h, fmt, n)
         frames = [make_frame(2, w, h, fmt, "noise", i) for i in range(n)]
@@ -136,7 +160,7 @@ def test_filter_object_properties():
         exp = O.oracle_frame(frames[3], 8, order=1, aa=20, dh=True)
         assert_planes_equal(planes[:3], exp[:3], "dh frame 3")
         assert np.array_equal(planes[3], np.repeat(frames[3][3], 2, axis=0))              # alpha: copied (row-doubled)
-    with FakeHost(has_v8=False) as host:
+    with FakeHost(cpu_flags=0, has_v8=False) as host:
         host.load_plugin(OURS)
         src = host.source(w, h, fmt, 1)
         src.set_frame(0, frames[0])
@@ -152,7 +176,7 @@ def test_batched_prefetch_and_seek(monkeypatch):
     w, h, n = 64, 32, 10
     frames = [make_frame(6, w, h, fmt, "edges", i) for i in range(n)]
     exp = [O.oracle_frame(fr, 8, order=0, parity=parity_of(i))[0] for i, fr in enumerate(frames)]
-    with FakeHost() as host:
+    with FakeHost(cpu_flags=0) as host:
         host.load_plugin(OURS)
         src = host.source(w, h, fmt, n, parity_mode=2)
         for i, fr in enumerate(frames):
@@ -180,7 +204,7 @@ def test_next_batch_is_prefetched_asynchronously(monkeypatch):
     w, h, n = 96, 64, 19
     frames = [make_frame(8, w, h, fmt, "noise", i) for i in range(n)]
     exp = [O.oracle_frame(fr, 8, order=0, aa=48, aac=48, parity=parity_of(i)) for i, fr in enumerate(frames)]
-    with FakeHost() as host:
+    with FakeHost(cpu_flags=0) as host:
         host.load_plugin(OURS)
         src = host.source(w, h, fmt, n, parity_mode=2)
         for i, fr in enumerate(frames):
@@ -197,3 +221,28 @@ def test_next_batch_is_prefetched_asynchronously(monkeypatch):
         for i in range(4, 12):
             assert_planes_equal(flt.get_frame(i)[:3], exp[i][:3], f"frame {i} again")
         # leave with a batch in flight: the destructor must wait for it
+
+
+def test_prefetch_failure_does_not_fail_a_finished_frame(monkeypatch):
+    """An error while fetching LATER frames for the speculative next batch must not fail the GetFrame whose own frame
+    is finished; it surfaces when one of those frames is requested, and the filter keeps working afterwards."""
+    from fakehost import AvisynthError
+    monkeypatch.setenv("SANGNOM_B200_BATCH", "4")
+    fmt = FORMATS["Y8"]
+    w, h, n = 64, 32, 12
+    frames = [make_frame(9, w, h, fmt, "edges", i) for i in range(n)]
+    exp = [O.oracle_frame(fr, 8, order=1)[0] for fr in frames]
+    with FakeHost(cpu_flags=0) as host:
+        host.load_plugin(OURS)
+        src = host.source(w, h, fmt, n)
+        for i, fr in enumerate(frames):
+            src.set_frame(i, fr)
+        src.fail_at(5)
+        flt = host.invoke("SangNom2", src)
+        for i in range(4):                                  # batch 0; its prefetch of 4..7 hits the failing frame
+            assert np.array_equal(flt.get_frame(i)[0], exp[i])
+        with pytest.raises(AvisynthError, match="injected failure at frame 5"):
+            flt.get_frame(4)
+        src.fail_at(-1)
+        for i in range(4, n):
+            assert np.array_equal(flt.get_frame(i)[0], exp[i])

@@ -14,7 +14,7 @@ from kat import KAT_IN, KATS
 from oracle import oracle as O
 from pysangnom import cuda
 from pysangnom.clips import make_frame
-from pysangnom.fakehost import FORMATS
+from pysangnom.formats import FORMATS
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 EMUL = os.path.join(HERE, "emul", "libkernel_emul.so")

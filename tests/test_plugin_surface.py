@@ -5,7 +5,8 @@ import os
 import pytest
 
 from oracle import oracle as O
-from pysangnom.fakehost import CPUF_SSE2, FORMATS, AvisynthError, FakeHost
+from pysangnom.formats import FORMATS
+from fakehost import CPUF_SSE2, AvisynthError, FakeHost
 
 PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "avisynth-sangnom2_b200")
 OURS = os.path.join(PKG, "libsangnom2_b200.so")

@@ -36,7 +36,7 @@ def _worker(rank, world, port, total, q):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "avisynth-sangnom2_b200")]
     from oracle import oracle as O
     from pysangnom.clips import make_frame
-    from pysangnom.fakehost import FORMATS
+    from pysangnom.formats import FORMATS
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -78,7 +78,7 @@ def test_two_ranks_cover_the_clip_once():
     sys.path[:0] = [ROOT]
     from oracle import oracle as O
     from pysangnom.clips import make_frame
-    from pysangnom.fakehost import FORMATS
+    from pysangnom.formats import FORMATS
     for n in range(total):
         out = O.oracle_frame(make_frame(9, 64, 32, FORMATS["YV12"], "noise", n), 8, order=0, aa=48, aac=48, parity=(n % 2 == 0))
         h = hashlib.sha256(b"".join(p.tobytes() for p in out)).digest()

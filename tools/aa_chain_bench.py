@@ -16,7 +16,7 @@ import numpy as np
 import torch
 from pysangnom import cuda
 from pysangnom.clips import make_frame
-from pysangnom.fakehost import FORMATS
+from pysangnom.formats import FORMATS
 
 frames_n = int(sys.argv[1]) if len(sys.argv) > 1 else 144
 fmt, w, h = FORMATS["YUV444P16"], 1920, 1080

@@ -6,7 +6,7 @@ import numpy as np, torch
 import bench
 from pysangnom import cuda
 from pysangnom.clips import make_frame
-from pysangnom.fakehost import FORMATS
+from pysangnom.formats import FORMATS
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "1080p8"
 Fe = int(sys.argv[2]) if len(sys.argv) > 2 else 592

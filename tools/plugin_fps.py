@@ -3,11 +3,12 @@
 PAGEABLE host frames, as a frame server would drive it. One filter instance (MT_NICE_FILTER), sequential pulls."""
 import ctypes as C, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "avisynth-sangnom2_b200")]
+sys.path[:0] = [ROOT, os.path.join(ROOT, "avisynth-sangnom2_b200"), os.path.join(ROOT, "tests")]
 import bench
 from pysangnom.clips import make_frame
-from pysangnom.fakehost import FORMATS, FakeHost
-from pysangnom import fakehost as fh
+from pysangnom.formats import FORMATS
+from fakehost import FakeHost
+import fakehost as fh
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "1080p8"
 batch = sys.argv[2] if len(sys.argv) > 2 else "64"
