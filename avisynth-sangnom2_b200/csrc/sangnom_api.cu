@@ -75,6 +75,7 @@ struct Pass {
     const sn_plane_job* job;
     int W, H, n;             // samples, rows, kept rows
     int R;                   // pool rows to sweep
+    int cone;                // dependency-cone bound (sangnom_plan.h)
     sn::CostState in{}, out{};
     // host path: how the kept field gets up and the finished plane gets down.
     //   STAGED  pageable host memory: CPU packs rows into the slot's pinned staging, one contiguous DMA
@@ -279,7 +280,7 @@ int plan_frames(sn_ctx* ctx, const sn_plane_job* jobs, int njobs, bool device_en
         sn::PassGeometry geo[3];
         for (int q = 0; q < m; ++q) { geo[q] = sn::PassGeometry{}; geo[q].width = f.passes[q].W; geo[q].kept_rows = f.passes[q].n; }
         f.state_bytes = sn::plan_frame_passes(geo, m, ctx->S, ctx->Hb, sb, ctx->persistent);
-        for (int q = 0; q < m; ++q) { f.passes[q].R = geo[q].sweep_rows; f.passes[q].in = geo[q].in; f.passes[q].out = geo[q].out; }
+        for (int q = 0; q < m; ++q) { f.passes[q].R = geo[q].sweep_rows; f.passes[q].cone = geo[q].cone; f.passes[q].in = geo[q].in; f.passes[q].out = geo[q].out; }
     }
     return SN_OK;
 }
@@ -315,7 +316,7 @@ sn::PlaneTask make_task(const sn_ctx* ctx, const Pass& p, void* plane, size_t pi
     // in place when the kept rows already sit at rows offset, offset+2, .. of the dst plane
     t.copy_kept = !(kept0 == static_cast<char*>(plane) + (size_t)p.job->offset * pitch_bytes && kept_step_bytes == 2 * pitch_bytes);
     t.width = p.W; t.height = p.H; t.offset = p.job->offset;
-    t.kept_rows = p.n; t.sweep_rows = p.R;
+    t.kept_rows = p.n; t.sweep_rows = p.R; t.cone = p.cone;
     t.thr_f = p.job->threshold;
     // `const T aaf` (reference SangNom2.cpp:162,272): float -> T for integer samples. Truncate
     // toward zero, then wrap to the container width - what x86-64 does for the (undefined in C++)
@@ -489,6 +490,12 @@ int sangnom_cuda_create(const sn_config* cfg, sn_ctx** out)
     if (S > sn::max_pool_width(cfg->sample_type)) {
         char b[160];
         snprintf(b, sizeof b, "pool width %d exceeds the supported maximum %d for %d-byte samples", S, sn::max_pool_width(cfg->sample_type), cfg->sample_type);
+        g_create_error = b;
+        return SN_ERR_UNSUPPORTED;
+    }
+    if (!sn::pool_width_supported(cfg->sample_type, S)) {
+        char b[200];
+        snprintf(b, sizeof b, "pool width %d (from clip width %d) is not supported: 8-bit pools wider than 8192 samples must be a multiple of 64", S, cfg->pool_width);
         g_create_error = b;
         return SN_ERR_UNSUPPORTED;
     }

@@ -18,6 +18,7 @@ inline void store_remote(V* local_ptr, unsigned target_rank, V value)
     const size_t off = reinterpret_cast<unsigned char*>(local_ptr) - emul::smem;
     *reinterpret_cast<V*>(emul::cluster_smem[target_rank] + off) = value;
 }
+inline void store_remote4(uint4* local_ptr, unsigned target_rank, uint4 value) { store_remote(local_ptr, target_rank, value); }
 #else
 __device__ __forceinline__ unsigned rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
@@ -43,6 +44,14 @@ __device__ __forceinline__ void store_remote(V* local_ptr, unsigned target_rank,
         memcpy(&bits, &value, 2);
         asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(remote), "h"(bits) : "memory");
     }
+}
+// the same for one 16-byte vector (16-byte aligned)
+__device__ __forceinline__ void store_remote4(uint4* local_ptr, unsigned target_rank, uint4 value)
+{
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(local_ptr);
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(target_rank));
+    asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "r"(value.x), "r"(value.y), "r"(value.z), "r"(value.w) : "memory");
 }
 #endif
 

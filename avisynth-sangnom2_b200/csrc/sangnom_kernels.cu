@@ -57,12 +57,18 @@ cudaError_t launch_clustered(K kernel, int blocks, int threads, size_t smem, int
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-// Smallest power-of-two split (<= 8 blocks) that brings a segment down to seg_max columns.
-int cluster_split(int S, int seg_max)
+// Split of a pool row over the blocks of a cluster: the smallest power of two (<= 8 blocks) that brings a segment down
+// to seg_pref columns with whole threads (cols_per_thread columns each); if that does not exist, the largest split
+// whose segments are whole threads and fit a block (seg_hard). 0 = this pool width cannot run.
+int cluster_split(int S, int seg_pref, int seg_hard, int cols_per_thread)
 {
-    int G = 1;
-    while (S / G > seg_max && G < 8) G *= 2;
-    return G;
+    int fallback = 0;
+    for (int G = 1; G <= 8; G *= 2) {
+        if (S % G != 0 || (S / G) % cols_per_thread != 0 || S / G > seg_hard) continue;
+        if (S / G <= seg_pref) return G;
+        fallback = G;
+    }
+    return fallback;
 }
 
 // One instantiation per (split over a cluster?, arithmetic flavour, spare threads?); shared-memory opt-in remembered per device.
@@ -85,9 +91,9 @@ cudaError_t launch_u8_variant(const PlaneTask* tasks, int ntasks, LaunchGeometry
 cudaError_t launch_u8(const PlaneTask* tasks, int ntasks, LaunchGeometry g, cudaStream_t stream)
 {
     const int seg_max = std::min(std::max(env_int("SANGNOM_U8_SEG", 2048), 256), 2048);     // tuning / test knob, read per launch: small values force cluster splits at small sizes
-    const int G = cluster_split(g.S, seg_max);
+    const int G = cluster_split(g.S, seg_max, 2048, u8k::kCols);
+    if (G == 0) return cudaErrorInvalidValue;
     const int seg = g.S / G;
-    if (seg > 2048 || seg % u8k::kCols != 0) return cudaErrorInvalidValue;
     if (G == 1) {
         if (g.narrow && seg / u8k::kCols < 256)
             return g.saturate ? launch_u8_variant<false, true, true>(tasks, ntasks, g, G, seg, stream) : launch_u8_variant<false, false, true>(tasks, ntasks, g, G, seg, stream);
@@ -96,15 +102,18 @@ cudaError_t launch_u8(const PlaneTask* tasks, int ntasks, LaunchGeometry g, cuda
     return g.saturate ? launch_u8_variant<true, true, false>(tasks, ntasks, g, G, seg, stream) : launch_u8_variant<true, false, false>(tasks, ntasks, g, G, seg, stream);
 }
 
-template <typename T, bool kClustered, bool kSat>
+template <typename T, bool kClustered, bool kSat, bool kSpare>
 cudaError_t launch_wide_variant(const PlaneTask* tasks, int ntasks, LaunchGeometry g, int G, int seg, cudaStream_t stream)
 {
     static size_t configured[64] = {};
-    auto kernel = wide::sangnom_wide_row_sweep<T, 256, 2, kClustered, kSat>;
+    auto kernel = wide::sangnom_wide_row_sweep<T, 256, 2, kClustered, kSat, kSpare>;
     const size_t smem = wide::smem_bytes<T>(seg);
     cudaError_t e = ensure_smem(kernel, smem, configured);
     if (e != cudaSuccess) return e;
-    return launch_clustered(kernel, ntasks * G, seg / wide::kCols, smem, G, stream, tasks, g, seg);
+    // kSpare: as for the 8-bit kernel - spare threads so that the last pixel thread of a narrow plane ends a warp
+    const int T_ = seg / wide::kCols;
+    const int threads = kSpare ? std::max(T_, std::min(256, ((T_ + 31) & ~31) + 32)) : T_;
+    return launch_clustered(kernel, ntasks * G, threads, smem, G, stream, tasks, g, seg);
 }
 
 // 16-bit / fp32: 4 columns per thread, at most 1024 columns per block. fp32 has one flavour (the SSE2 path computes the
@@ -113,20 +122,30 @@ template <typename T>
 cudaError_t launch_wide(const PlaneTask* tasks, int ntasks, LaunchGeometry g, cudaStream_t stream)
 {
     const int seg_max = std::min(std::max(env_int("SANGNOM_WIDE_SEG", 1024), 128), 1024);   // tuning / test knob, read per launch
-    const int G = cluster_split(g.S, seg_max);
+    const int G = cluster_split(g.S, seg_max, 1024, wide::kCols);
+    if (G == 0) return cudaErrorInvalidValue;
     const int seg = g.S / G;
-    if (seg > 1024 || seg % wide::kCols != 0) return cudaErrorInvalidValue;
     constexpr bool kInt = !Flavour<T>::kFloat;
+    const bool spare = G == 1 && g.narrow && seg / wide::kCols < 256;
     if constexpr (kInt) {
-        if (g.saturate)
-            return G == 1 ? launch_wide_variant<T, false, true>(tasks, ntasks, g, G, seg, stream) : launch_wide_variant<T, true, true>(tasks, ntasks, g, G, seg, stream);
+        if (g.saturate) {
+            if (G != 1) return launch_wide_variant<T, true, true, false>(tasks, ntasks, g, G, seg, stream);
+            return spare ? launch_wide_variant<T, false, true, true>(tasks, ntasks, g, G, seg, stream) : launch_wide_variant<T, false, true, false>(tasks, ntasks, g, G, seg, stream);
+        }
     }
-    return G == 1 ? launch_wide_variant<T, false, false>(tasks, ntasks, g, G, seg, stream) : launch_wide_variant<T, true, false>(tasks, ntasks, g, G, seg, stream);
+    if (G != 1) return launch_wide_variant<T, true, false, false>(tasks, ntasks, g, G, seg, stream);
+    return spare ? launch_wide_variant<T, false, false, true>(tasks, ntasks, g, G, seg, stream) : launch_wide_variant<T, false, false, false>(tasks, ntasks, g, G, seg, stream);
 }
 
 }  // namespace
 
 int max_pool_width(int sample_bytes) { return sample_bytes == 1 ? 8 * 2048 : 8 * 1024; }
+
+bool pool_width_supported(int sample_bytes, int S)
+{
+    if (S <= 0 || S % 32 != 0 || S > max_pool_width(sample_bytes)) return false;
+    return sample_bytes == 1 ? cluster_split(S, 2048, 2048, u8k::kCols) != 0 : cluster_split(S, 1024, 1024, wide::kCols) != 0;
+}
 
 const char* kernel_variant_name(int sample_bytes, int S)
 {

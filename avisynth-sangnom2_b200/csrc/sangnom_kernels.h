@@ -36,8 +36,12 @@ struct PlaneTask {
     int sweep_rows;         // R >= n-1: pool rows to run the cost recursion over
     int thr_i;              // threshold truncated to the sample type (integer flavours)
     float thr_f;            // fp32 flavour
+    int cone;               // dependency cone of everything downstream of this pass (sangnom_plan.h): at pool row r only the
+                            // columns < cone - 3r can still reach a picture sample of this or a later pass of the frame;
+                            // threads beyond it have nothing left to do. kNoCone: sweep everything (persistent pool).
     CostState in, out;      // cost state from the previous pass / for the next pass of this frame
 };
+constexpr int kNoCone = 1 << 29;
 
 struct LaunchGeometry {
     int S;                  // pool row length in samples (align32 of the output luma width)
@@ -55,6 +59,9 @@ inline LaunchGeometry make_geometry(int S, int Hb, bool saturate = false, bool n
 
 // Widest pool each sample type can run (columns per thread x max threads per block).
 int max_pool_width(int sample_bytes);
+// Whether a pool row of S samples can be split into whole-thread column segments that fit a block (8-bit pools wider
+// than 8192 need S % 64 == 0).
+bool pool_width_supported(int sample_bytes, int S);
 
 // Launch one block per task. `tasks_dev` is a device array of ntasks PlaneTask.
 // Returns cudaSuccess or the launch error. sample_bytes in {1,2,4}.

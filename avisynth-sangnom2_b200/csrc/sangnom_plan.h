@@ -10,6 +10,12 @@
 //   * a cell pass q reads at pool row r must have been swept by every earlier pass of the frame,
 //     so earlier passes may have to sweep more rows than their own picture needs (sweep_rows);
 //   * pass q hands pass q+1 exactly the cells q+1 will read outside its rectangle (CostState).
+//   * of those cells only the ones inside the dependency cone of a picture sample matter. The recursion reaches 3
+//     columns sideways per row (:144-152), so a cell at pool row r, column c can influence a sample of a plane of
+//     width W with n kept rows only if c < W + 3 (n - 1 - r) + (what the later passes need through the hand-over, 6
+//     columns per pass). Every pass gets that bound as `cone`: the columns it has to work on at row r are those
+//     below cone - 3r; the warps right of it retire, and nothing is exported from there. Exactness is not touched:
+//     the cells left out cannot reach any output.
 #pragma once
 #include <algorithm>
 #include <cstddef>
@@ -23,6 +29,7 @@ struct PassGeometry {
     int width;        // W: picture columns of this plane
     int kept_rows;    // n = H/2
     int sweep_rows;   // out: R
+    int cone;         // out: see PlaneTask::cone
     CostState in, out;   // out: regions; pointers hold (byte offset + 1) into the frame's state scratch, 0 = empty
 };
 
@@ -41,6 +48,13 @@ inline size_t plan_frame_passes(PassGeometry* passes, int m, int S, int Hb, int 
         p.sweep_rows = std::min(p.kept_rows - 1, Hb - 1);
         if (persistent && q == m - 1) p.sweep_rows = std::max(p.sweep_rows, Hb - 1);
         if (q + 1 < m) p.sweep_rows = std::max(p.sweep_rows, std::min(Hb - 1, passes[q + 1].sweep_rows + 1));
+        // Columns of blurred row r that are still needed: need(r) = max(W [r <= n-1], what pass q+1 reads of row r,
+        // need(r+1) + 3). Pass q+1 reads its stale input P[r] up to 3 columns right of what it computes at rows r-1
+        // and r, so the bound grows by 6 per pass. All terms are lines of slope -3 in r. A thread must still be there
+        // at row r if it owns a column of the vertical sums L[r] that a needed cell reads: column < need(r) + 3.
+        p.cone = p.width + 3 * p.kept_rows;
+        if (q + 1 < m) p.cone = std::max(p.cone, passes[q + 1].cone + 6);
+        if (persistent) p.cone = kNoCone;
     }
     size_t off = 0;
     for (int q = 0; q + 1 < m; ++q) {

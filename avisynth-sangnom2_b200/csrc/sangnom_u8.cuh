@@ -282,8 +282,9 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
         return;
     }
     // (spare lanes have exited: the warp votes below may still name them in their mask)
+    const int wfirst = max((hw & ~31) - shift, 0);                  // first working thread of my warp
 #ifdef SN_HOST_EMULATION
-    const int wfirst = max((hw & ~31) - shift, 0), wlast = min((hw & ~31) + 31 - shift, T - 1);       // working thread range of my "warp"
+    const int wlast = min((hw & ~31) + 31 - shift, T - 1);          // the emulation has no warps: working thread range of my "warp"
 #endif
     const int lx = tid * kCols;                                     // column inside the segment
     const int x0 = seg_x0 + lx;                                     // pool column
@@ -434,6 +435,10 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     if constexpr (kClustered) cl::sync_all();
 
     const uint32_t tkey = (uint32_t)min(t.thr_i + 1, 4095) * 0x00100010u;    // (thr+1) << 4 in both lanes
+    // Dependency cone (sangnom_plan.h): at pool row r only columns < cone - 3r can still reach a picture sample of this
+    // or a later pass of the frame. A warp whose first column lies beyond that has nothing left to do - it leaves, the
+    // row barriers go on without it (warps with pixel columns stay to the last picture row by construction).
+    const int r_last = min(R, (t.cone - 1 - (seg_x0 + wfirst * kCols)) / 3);
 
     // One pool row. kFull: every thread of the warp owns 8 pixel columns (no stale-state or masking code on the hot
     // path). kPair: row r+1 is a pair row (r + 1 <= n - 1), i.e. its costs come from pixels.
@@ -510,7 +515,8 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
             for (int i = 0; i < kNumCost; ++i) {
                 const uint2 Lzw = Lrow[2 * i + 1];
                 if (plane_last) { const uint32_t e = (Lzw.y >> 16) * 0x00010001u; Lrow[2 * i + kLEntry] = make_uint2(e, e); }
-                else {
+                else if (3 * r + seg_x0 + seg_cols < t.cone) {              // the block right of mine is still there: once its first column is outside
+                                                                            // the cone it has exited, and DSMEM of an exited block must not be written
                     cl::store_remote(&Lrow[2 * i + 1 - T * kLEntry].x, crank + 1, Lzw.x);
                     cl::store_remote(&Lrow[2 * i + 1 - T * kLEntry].y, crank + 1, Lzw.y);
                 }
@@ -608,17 +614,23 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     auto sweep = [&](auto full) {
         int r = 1;
         StateRow out;
-        for (; r <= n - 2; ++r) {                                           // rows whose lower neighbour row is a pair row
+        for (; r <= n - 2 && r <= r_last; ++r) {                            // rows whose lower neighbour row is a pair row
             if (export_row(r, out)) row_step(full, std::true_type{}, std::true_type{}, r, out);
             else row_step(full, std::true_type{}, std::false_type{}, r, out);
         }
-        for (; r <= R; ++r) {                                               // the last picture row and rows swept for the next pass only
+        for (; r <= r_last; ++r) {                                          // the last picture row and rows swept for the next pass only
             if (export_row(r, out)) row_step(full, std::false_type{}, std::true_type{}, r, out);
             else row_step(full, std::false_type{}, std::false_type{}, r, out);
         }
     };
     // warp-uniform choice, so that a warp never splits over the two copies of the row barrier
     if (warp_full) sweep(std::true_type{}); else sweep(std::false_type{});
+#ifdef SN_HOST_EMULATION
+    if (r_last < R) {                                                       // left before the last row: out of the barriers
+        emul::bar->arrive_and_drop();
+        if (kClustered) emul::cluster_bar->arrive_and_drop();
+    }
+#endif
 }
 
 }  // namespace u8k

@@ -82,6 +82,7 @@ inline uint32_t __vminu2(uint32_t a, uint32_t b) { return std::min(a & 0xFFFFu, 
 inline uint32_t __vimin3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vminu2(__vminu2(a, b), c); }
 inline uint32_t __vimin3_u32(uint32_t a, uint32_t b, uint32_t c) { return std::min(std::min(a, b), c); }
 inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }

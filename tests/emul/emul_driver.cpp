@@ -47,7 +47,7 @@ int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long lo
             t.copy_kept = 0;
         }
         t.width = widths[q]; t.height = heights[q]; t.offset = offsets[q];
-        t.kept_rows = geo[q].kept_rows; t.sweep_rows = geo[q].sweep_rows;
+        t.kept_rows = geo[q].kept_rows; t.sweep_rows = geo[q].sweep_rows; t.cone = geo[q].cone;
         t.thr_f = thresholds[q];
         t.thr_i = sample_bytes == 1 ? ((int)thresholds[q] & 0xFF) : ((int)thresholds[q] & 0xFFFF);
         t.in = geo[q].in; t.out = geo[q].out;
@@ -58,27 +58,24 @@ int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long lo
         if (S % (int)(G * cols) != 0) return -1;
         const int seg = S / (int)G;
         unsigned threads = (unsigned)(seg / cols);
-        const bool spare_threads = sample_bytes == 1 && G == 1 && narrow && threads < 256;
+        const bool spare_threads = G == 1 && narrow && threads < 256;
         if (spare_threads) threads = std::max(threads, std::min(256u, ((threads + 31u) & ~31u) + 32u));      // like the launcher
-        // one block per plane runs the unclustered instantiation, like the launcher (it alone has the helper-lane path)
-        if (spare_threads && saturate)
-            emul::run_cluster(0, G, threads, sn::u8k::smem_bytes(seg), [&] { sn::u8k::sangnom_u8_row_sweep<1024, 1, false, true, true>(&t, g, seg); });
-        else if (spare_threads)
-            emul::run_cluster(0, G, threads, sn::u8k::smem_bytes(seg), [&] { sn::u8k::sangnom_u8_row_sweep<1024, 1, false, false, true>(&t, g, seg); });
-        else if (sample_bytes == 1 && saturate && G == 1)
-            emul::run_cluster(0, G, threads, sn::u8k::smem_bytes(seg), [&] { sn::u8k::sangnom_u8_row_sweep<1024, 1, false, true>(&t, g, seg); });
-        else if (sample_bytes == 1 && G == 1)
-            emul::run_cluster(0, G, threads, sn::u8k::smem_bytes(seg), [&] { sn::u8k::sangnom_u8_row_sweep<1024, 1, false>(&t, g, seg); });
-        else if (sample_bytes == 1 && saturate)
-            emul::run_cluster(0, G, threads, sn::u8k::smem_bytes(seg), [&] { sn::u8k::sangnom_u8_row_sweep<1024, 1, true, true>(&t, g, seg); });
-        else if (sample_bytes == 1)
-            emul::run_cluster(0, G, threads, sn::u8k::smem_bytes(seg), [&] { sn::u8k::sangnom_u8_row_sweep<1024, 1, true>(&t, g, seg); });
-        else if (sample_bytes == 2 && saturate)
-            emul::run_cluster(0, G, threads, sn::wide::smem_bytes<uint16_t>(seg), [&] { sn::wide::sangnom_wide_row_sweep<uint16_t, 1024, 1, true, true>(&t, g, seg); });
-        else if (sample_bytes == 2)
-            emul::run_cluster(0, G, threads, sn::wide::smem_bytes<uint16_t>(seg), [&] { sn::wide::sangnom_wide_row_sweep<uint16_t, 1024, 1, true>(&t, g, seg); });
-        else
-            emul::run_cluster(0, G, threads, sn::wide::smem_bytes<float>(seg), [&] { sn::wide::sangnom_wide_row_sweep<float, 1024, 1, true>(&t, g, seg); });
+        // one block per plane runs the unclustered instantiation, like the launcher (it alone has the spare-thread map)
+        auto run = [&](size_t smem, auto kernel) { emul::run_cluster(0, G, threads, smem, [&] { kernel(&t, g, seg); }); };
+        auto pick = [&](auto clustered, auto sat, auto spare) {
+            constexpr bool kC = decltype(clustered)::value, kS = decltype(sat)::value, kP = decltype(spare)::value;
+            if (sample_bytes == 1) run(sn::u8k::smem_bytes(seg), sn::u8k::sangnom_u8_row_sweep<1024, 1, kC, kS, kP>);
+            else if (sample_bytes == 2) run(sn::wide::smem_bytes<uint16_t>(seg), sn::wide::sangnom_wide_row_sweep<uint16_t, 1024, 1, kC, kS, kP>);
+            else run(sn::wide::smem_bytes<float>(seg), sn::wide::sangnom_wide_row_sweep<float, 1024, 1, kC, false, kP>);
+        };
+        using Y = std::true_type;
+        using N = std::false_type;
+        if (G == 1) {
+            if (spare_threads) { if (saturate) pick(N{}, Y{}, Y{}); else pick(N{}, N{}, Y{}); }
+            else { if (saturate) pick(N{}, Y{}, N{}); else pick(N{}, N{}, N{}); }
+        } else {
+            if (saturate) pick(Y{}, Y{}, N{}); else pick(Y{}, N{}, N{});
+        }
     }
     return 0;
 }

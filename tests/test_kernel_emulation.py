@@ -203,3 +203,21 @@ def test_wide_subsampled_planes(emul, fmtname, w, h, kw, kind, saturate):
         got = emulate(emul, fr, fmt.bits, parity=(i == 0), out_of_place=(i == 1), saturate=saturate, **kw)
         exp = O.oracle_frame(fr, fmt.bits, parity=(i == 0), saturate=saturate, **kw)
         assert_planes_equal(got, exp[:3], f"wide {fmtname} {w}x{h} {kw} frame {i}")
+
+
+# Planes tall and wide enough that warps (and, split over a cluster, whole blocks) right of the chroma rectangle retire
+# part-way down the sweep when their columns leave the dependency cone (sangnom_plan.h). The emulation poisons the
+# hand-over scratch and the shared memory, so a cone that is too tight shows up as wrong samples.
+CONE_CASES = [("YV12", 1600, 400, dict(order=0, aa=48, aac=48), 1), ("YV12", 1024, 400, dict(order=1, aa=48, aac=48), 4),
+              ("YV411", 1536, 120, dict(order=2, aa=48, aac=30), 1), ("YUV422P8", 1024, 200, dict(order=1, aa=20, aac=90), 2),
+              ("YUV420P16", 800, 400, dict(order=0, aa=48, aac=48), 1), ("YUV420PS", 512, 400, dict(order=2, aa=48, aac=24), 4),
+              ("YUV420P10", 1024, 240, dict(order=1, aa=48, aac=48), 8)]
+
+
+@pytest.mark.parametrize("fmtname,w,h,kw,cluster", CONE_CASES, ids=[f"{c[0]}_{c[1]}x{c[2]}_G{c[4]}" for c in CONE_CASES])
+def test_dependency_cone_trimming(emul, fmtname, w, h, kw, cluster):
+    fmt = FORMATS[fmtname]
+    fr = make_frame(211, w, h, fmt, "noise", 0)
+    got = emulate(emul, fr, fmt.bits, parity=False, cluster=cluster, **kw)
+    exp = O.oracle_frame(fr, fmt.bits, parity=False, **kw)
+    assert_planes_equal(got, exp[:3], f"cone {fmtname} {w}x{h} {kw} G={cluster}")
