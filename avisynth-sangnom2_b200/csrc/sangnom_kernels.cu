@@ -126,6 +126,7 @@ cudaError_t launch_wide(const PlaneTask* tasks, int ntasks, LaunchGeometry g, cu
     if (G == 0) return cudaErrorInvalidValue;
     const int seg = g.S / G;
     constexpr bool kInt = !Flavour<T>::kFloat;
+    g.key_mask = (unsigned)Flavour<T>::kMask << 4;                  // the key mask of the integer flavour (sangnom_wide.cuh)
     const bool spare = G == 1 && g.narrow && seg / wide::kCols < 256;
     if constexpr (kInt) {
         if (g.saturate) {

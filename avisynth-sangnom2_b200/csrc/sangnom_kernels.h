@@ -29,6 +29,8 @@ struct PlaneTask {
     const void* src;        // device pointer to kept row 0 (reference: the rows the BitBlt at GetFrame :361-377 copies)
     long long src_pitch;    // elements between consecutive kept rows. In place: src = plane + offset*pitch, src_pitch = 2*pitch
     int copy_kept;          // 1: the kept rows are not in the dst plane yet - the kernel writes them too
+    int no_border;          // 1: the row without a neighbour pair (reference GetFrame :380-391) is not written either: the host
+                            // path keeps kept rows and border row on the host and brings home only the interpolated rows
     int width;              // W: samples per row that carry pixels (cost rectangle width)
     int height;             // H: rows of the dst plane
     int offset;             // 0 / 1: first kept row

@@ -1,0 +1,428 @@
+// Host pipeline of one device (see sangnom_ctx.h for the shape of the host path).
+//
+// What crosses PCIe per processed plane is the minimum the reference's seam implies (/root/reference/src/
+// SangNom2.cpp:361-393): UP the kept field (the rows the BitBlt at :361-377 copies, W*H/2 samples), DOWN the
+// interpolated rows (W*(H/2-1) samples). The kept rows and the border row of the destination frame (:380-391) never
+// leave the host: they are copied source -> destination by the pipeline's copy pool while the DMA engines work.
+// The device holds, per plane, the uploaded kept rows and a packed block of interpolated rows; the kernel is pointed
+// at that block through a plane pointer / pitch pair under which picture row offset+1+2j is packed row j.
+#include "sangnom_ctx.h"
+
+#include <cuda.h>      // driver API types only; the entry point is looked up at run time (no libcuda link dependency)
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+
+namespace sn_host {
+
+// ---- PinnedLookup -------------------------------------------------------------------------------------------------
+namespace {
+using GetAttr = CUresult (*)(void*, CUpointer_attribute, CUdeviceptr);
+GetAttr driver_entry()          // looked up once per process
+{
+    static const GetAttr fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            return reinterpret_cast<GetAttr>(p);
+        cudaGetLastError();
+        return static_cast<GetAttr>(nullptr);
+    }();
+    return fn;
+}
+}  // namespace
+
+PinnedLookup::PinnedLookup() : get_(reinterpret_cast<void*>(driver_entry())) {}
+
+int PinnedLookup::find(const void* p)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    for (size_t i = 0; i < known_.size(); ++i)
+        if (a >= known_[i].lo && a < known_[i].hi) return (int)i + 1;
+    Range r;
+    if (get_) {
+        const GetAttr get = reinterpret_cast<GetAttr>(get_);
+        CUmemorytype type{};
+        CUdeviceptr base = 0;
+        size_t size = 0;
+        if (get(&type, CU_POINTER_ATTRIBUTE_MEMORY_TYPE, (CUdeviceptr)a) != CUDA_SUCCESS || type != CU_MEMORYTYPE_HOST) return 0;
+        if (get(&base, CU_POINTER_ATTRIBUTE_RANGE_START_ADDR, (CUdeviceptr)a) != CUDA_SUCCESS ||
+            get(&size, CU_POINTER_ATTRIBUTE_RANGE_SIZE, (CUdeviceptr)a) != CUDA_SUCCESS || size == 0) {
+            r.lo = a; r.hi = a + 1;            // pinned, extent unknown: never merged with anything
+        } else {
+            r.lo = (uintptr_t)base; r.hi = r.lo + size;
+        }
+    } else {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+        if (at.type != cudaMemoryTypeHost) return 0;
+        r.lo = a; r.hi = a + 1;
+    }
+    known_.push_back(r);
+    return (int)known_.size();
+}
+
+// ---- DMA runs -------------------------------------------------------------------------------------------------------
+namespace {
+
+// A run of bytes that is contiguous both in (pinned) host memory and in the device slot: one DMA transfer.
+struct Segment { char* host; char* dev; size_t bytes; int alloc; };
+
+// alloc: which pinned allocation `host` lies in (runs are merged only inside one allocation: a copy that spans two
+// cudaHostAlloc blocks fails even when they are neighbours in the address space)
+void add_segment(std::vector<Segment>& v, void* host, void* dev, size_t bytes, int alloc)
+{
+    if (bytes == 0) return;
+    char* h = static_cast<char*>(host);
+    char* d = static_cast<char*>(dev);
+    if (!v.empty() && v.back().alloc == alloc && v.back().host + v.back().bytes == h && v.back().dev + v.back().bytes == d) v.back().bytes += bytes;
+    else v.push_back(Segment{ h, d, bytes, alloc });
+}
+
+cudaError_t flush_segments(std::vector<Segment>& v, cudaMemcpyKind kind, cudaStream_t stream)
+{
+    cudaError_t e = cudaSuccess;
+    for (const Segment& g : v) {
+        e = kind == cudaMemcpyHostToDevice ? cudaMemcpyAsync(g.dev, g.host, g.bytes, kind, stream) : cudaMemcpyAsync(g.host, g.dev, g.bytes, kind, stream);
+        if (e != cudaSuccess) break;
+    }
+    v.clear();
+    return e;
+}
+
+const bool g_trace = getenv("SANGNOM_TRACE") != nullptr;
+
+// The kept rows of a job in host memory: first row and the step between consecutive kept rows (bytes).
+inline const char* kept_rows(const sn_plane_job& jb, ptrdiff_t& step)
+{
+    const bool field = jb.mode == SN_MODE_FIELD;
+    step = jb.src_pitch * (field ? 2 : 1);
+    return static_cast<const char*>(jb.src) + (field ? (ptrdiff_t)jb.offset * jb.src_pitch : 0);
+}
+
+}  // namespace
+
+// ---- Pipeline -------------------------------------------------------------------------------------------------------
+Pipeline::Pipeline(sn_ctx* ctx, int device, int copy_threads) : ctx_(ctx), device_(device), pool_(std::max(0, copy_threads - 1)) {}
+
+Pipeline::~Pipeline()
+{
+    stop_and_join();
+    cudaSetDevice(device_);
+    for (Slot& s : slots_) {
+        s.planes.release(); s.state.release(); s.tasks.release();
+        s.tasks_host.release(); s.stage_in.release(); s.stage_out.release();
+        if (s.compute) cudaStreamDestroy(s.compute);
+        for (cudaEvent_t e : { s.h2d_done, s.kernels_done, s.d2h_done, s.t_h2d0, s.t_k0, s.t_d2h0 })
+            if (e) cudaEventDestroy(e);
+    }
+    if (trace_base_) cudaEventDestroy(trace_base_);
+    if (h2d_) cudaStreamDestroy(h2d_);
+    if (d2h_) cudaStreamDestroy(d2h_);
+    cudaGetLastError();
+}
+
+cudaError_t Pipeline::init()
+{
+    cudaError_t e;
+    if ((e = cudaSetDevice(device_)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&h2d_, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&d2h_, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    for (Slot& s : slots_) {
+        if ((e = cudaStreamCreateWithFlags(&s.compute, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        for (cudaEvent_t* ev : { &s.h2d_done, &s.kernels_done, &s.d2h_done })
+            if ((e = cudaEventCreateWithFlags(ev, g_trace ? cudaEventDefault : cudaEventDisableTiming)) != cudaSuccess) return e;
+        if (g_trace)
+            for (cudaEvent_t* ev : { &s.t_h2d0, &s.t_k0, &s.t_d2h0 })
+                if ((e = cudaEventCreate(ev)) != cudaSuccess) return e;
+    }
+    if (g_trace) {
+        if ((e = cudaEventCreate(&trace_base_)) != cudaSuccess) return e;
+        cudaEventRecord(trace_base_, h2d_);
+    }
+    return cudaSuccess;
+}
+
+void Pipeline::start() { worker_ = std::thread([this] { run(); }); }
+
+void Pipeline::push(const Chunk& c)
+{
+    { std::lock_guard<std::mutex> lk(mu_); queue_.push_back(c); }
+    cv_.notify_one();
+}
+
+void Pipeline::stop_and_join()
+{
+    if (!worker_.joinable()) return;
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+    cv_.notify_one();
+    worker_.join();
+}
+
+void Pipeline::chunk_done(const Chunk& c, int status, const std::string& err)
+{
+    if (status != SN_OK) c.batch->fail(status, err);
+    else {
+        std::lock_guard<std::mutex> lk(ctx_->stats_mu);
+        ctx_->stats.frames += c.last - c.first;
+    }
+    if (c.batch->chunks_left.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+        std::lock_guard<std::mutex> lk(ctx_->mu);          // the waiter checks chunks_left under this lock
+        ctx_->done_cv.notify_all();
+    }
+}
+
+void Pipeline::run()
+{
+    cudaSetDevice(device_);
+    for (;;) {
+        Chunk c;
+        bool have = false;
+        bool any_busy = false;
+        for (const Slot& s : slots_) any_busy = any_busy || s.busy;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            if (!any_busy) cv_.wait(lk, [&] { return stop_ || !queue_.empty(); });
+            if (!queue_.empty()) { c = queue_.front(); queue_.pop_front(); have = true; }
+            else if (stop_ && !any_busy) return;
+        }
+        std::string err;
+        if (have) {
+            Slot& s = slots_[next_slot_];
+            next_slot_ = (next_slot_ + 1) % kSlots;
+            if (s.busy) {                                   // the oldest chunk in flight: its buffers are needed
+                const Chunk old = s.chunk;
+                const int rc = finish_slot(s, err);
+                chunk_done(old, rc, err);
+                err.clear();
+            }
+            const int rc = start_chunk(s, c, err);
+            if (rc != SN_OK) chunk_done(c, rc, err);
+        } else {
+            // nothing queued: bring the oldest chunk in flight home
+            for (int k = 0; k < kSlots; ++k) {
+                Slot& s = slots_[(next_slot_ + k) % kSlots];
+                if (!s.busy) continue;
+                const Chunk old = s.chunk;
+                const int rc = finish_slot(s, err);
+                chunk_done(old, rc, err);
+                break;
+            }
+        }
+    }
+}
+
+#define PL_CUDA(call, what)                                                                          \
+    do {                                                                                             \
+        const cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) { err = std::string(what) + ": " + cudaGetErrorString(e__); status = SN_ERR_CUDA; break; } \
+    } while (0)
+
+int Pipeline::start_chunk(Slot& s, const Chunk& c, std::string& err)
+{
+    sn_ctx* const ctx = ctx_;
+    const int sb = ctx->sample_bytes;
+    std::vector<FramePlan>& frames = c.batch->frames;
+    int status = SN_OK;
+
+    // ---- placement inside the slot: one region for the uploaded kept rows and one for the packed interpolated rows,
+    // each filled in job order at 16 / 32-byte granules, so that planes which are neighbours inside one pinned host
+    // allocation (or in the slot's own staging) are neighbours on the device and their DMA transfers merge into one
+    size_t src_total = 0, out_total = 0, state_bytes = 0, in_bytes = 0, out_bytes = 0, ntasks = 0;
+    for (size_t k = c.first; k < c.last; ++k) {
+        FramePlan& f = frames[k];
+        f.state_off = state_bytes;
+        state_bytes += align_up(f.state_bytes, 256);
+        for (Pass& p : f.passes) {
+            const sn_plane_job& jb = *p.job;
+            const size_t row = (size_t)p.W * sb;
+            if (!p.src_pinned) { p.up = Pass::STAGED; p.src_pitch = align_up(row, 16); p.stage_in_off = in_bytes; in_bytes += p.src_pitch * p.n; }
+            else if (jb.mode != SN_MODE_FIELD && (size_t)jb.src_pitch == row && row % 16 == 0) { p.up = Pass::LINEAR; p.src_pitch = row; }
+            else { p.up = Pass::PITCHED; p.src_pitch = align_up(row, 16); }
+            p.src_off = src_total; src_total += p.src_pitch * p.n;
+            // 32-byte rows: half a row (the pitch the kernel is given, see below) stays a multiple of its widest store
+            p.out_pitch = align_up(row, 32);
+            p.out_off = out_total; out_total += p.out_pitch * (size_t)(p.n - 1);
+            if (!p.dst_pinned) { p.down = Pass::STAGED; p.stage_out_off = out_bytes; out_bytes += p.out_pitch * (size_t)(p.n - 1); }
+            else p.down = Pass::PITCHED;
+            ++ntasks;
+        }
+    }
+    // the kernel's border-row store is switched off (no_border), but rows are addressed relative to a pointer two
+    // packed half-rows before the block: keep a margin in front of it inside the allocation
+    const size_t out_base = align_up(src_total, 256) + 256;
+    const size_t plane_bytes = out_base + out_total + 256;
+
+    do {
+        cudaError_t e;
+        if ((e = s.planes.ensure(plane_bytes)) != cudaSuccess || (e = s.state.ensure(state_bytes)) != cudaSuccess ||
+            (e = s.tasks.ensure(ntasks * sizeof(sn::PlaneTask))) != cudaSuccess ||
+            (e = s.tasks_host.ensure(ntasks * sizeof(sn::PlaneTask))) != cudaSuccess ||
+            (e = s.stage_in.ensure(in_bytes)) != cudaSuccess || (e = s.stage_out.ensure(out_bytes)) != cudaSuccess) {
+            err = std::string("slot allocation: ") + cudaGetErrorString(e);
+            status = (e == cudaErrorMemoryAllocation) ? SN_ERR_NOMEM : SN_ERR_CUDA;
+            cudaGetLastError();
+            break;
+        }
+        char* const dplanes = static_cast<char*>(s.planes.p);
+
+        // ---- host-side copies of the chunk, all at once on the copy pool: the kept rows and the border row of every
+        // destination plane (reference :361-391), the planes that are only copied (disabled planes, alpha, :369-374),
+        // and the kept rows of pageable sources into the pinned staging buffer
+        uint64_t host_bytes = 0;
+        {
+            std::vector<RowCopy> copies;
+            for (size_t k = c.first; k < c.last; ++k) {
+                FramePlan& f = frames[k];
+                for (const sn_plane_job* cj : f.copies) {
+                    if (cj->src == cj->dst) continue;
+                    copies.push_back(RowCopy{ static_cast<char*>(cj->dst), static_cast<const char*>(cj->src), cj->dst_pitch, cj->src_pitch, (size_t)cj->width * sb, cj->dst_height });
+                    host_bytes += (uint64_t)cj->width * sb * cj->dst_height;
+                }
+                for (Pass& p : f.passes) {
+                    const sn_plane_job& jb = *p.job;
+                    const size_t row = (size_t)p.W * sb;
+                    ptrdiff_t step;
+                    const char* kept = kept_rows(jb, step);
+                    char* const dst = static_cast<char*>(jb.dst);
+                    char* const dkept = dst + (ptrdiff_t)jb.offset * jb.dst_pitch;
+                    if (!(kept == dkept && step == 2 * jb.dst_pitch)) {          // not already in place in the destination frame
+                        copies.push_back(RowCopy{ dkept, kept, 2 * jb.dst_pitch, step, row, p.n });
+                        host_bytes += (uint64_t)row * p.n;
+                    }
+                    // the row without a neighbour pair: a copy of the nearest kept row (:380-391)
+                    if (jb.offset == 0) copies.push_back(RowCopy{ dst + (ptrdiff_t)(p.H - 1) * jb.dst_pitch, kept + (ptrdiff_t)(p.n - 1) * step, 0, 0, row, 1 });
+                    else copies.push_back(RowCopy{ dst, kept, 0, 0, row, 1 });
+                    if (p.up == Pass::STAGED) {
+                        copies.push_back(RowCopy{ static_cast<char*>(s.stage_in.p) + p.stage_in_off, kept, (ptrdiff_t)p.src_pitch, step, row, p.n });
+                        host_bytes += (uint64_t)row * p.n;
+                    }
+                }
+            }
+            pool_.run(copies);
+        }
+
+        // ---- upload of the kept rows ----
+        uint64_t h2d_bytes = 0, d2h_bytes = 0;
+        if (g_trace) cudaEventRecord(s.t_h2d0, h2d_);
+        std::vector<std::vector<sn::PlaneTask>> by_pass;
+        std::vector<Segment> up_segs, down_segs;
+        for (size_t k = c.first; k < c.last && status == SN_OK; ++k) {
+            FramePlan& f = frames[k];
+            place_state(ctx, f, static_cast<char*>(s.state.p) + f.state_off);
+            for (size_t q = 0; q < f.passes.size(); ++q) {
+                Pass& p = f.passes[q];
+                const sn_plane_job& jb = *p.job;
+                const size_t row = (size_t)p.W * sb;
+                ptrdiff_t step;
+                const char* kept = kept_rows(jb, step);
+                char* const dsrc = dplanes + p.src_off;
+                if (p.up == Pass::STAGED) add_segment(up_segs, static_cast<char*>(s.stage_in.p) + p.stage_in_off, dsrc, p.src_pitch * p.n, -1);
+                else if (p.up == Pass::LINEAR) add_segment(up_segs, const_cast<char*>(kept), dsrc, row * p.n, p.src_pinned);
+                else {
+                    PL_CUDA(flush_segments(up_segs, cudaMemcpyHostToDevice, h2d_), "H2D copy");           // keep submission order
+                    PL_CUDA(cudaMemcpy2DAsync(dsrc, p.src_pitch, kept, (size_t)step, row, (size_t)p.n, cudaMemcpyHostToDevice, h2d_), "H2D copy");
+                }
+                h2d_bytes += p.up == Pass::PITCHED ? row * p.n : p.src_pitch * p.n;
+                // Picture row offset+1+2j of the plane is packed row j of the block at out_off: hand the kernel a pitch of
+                // half a packed row and a plane pointer (offset+1) half-rows before the block.
+                char* const dout = dplanes + out_base + p.out_off;
+                const size_t half = p.out_pitch / 2;
+                add_task(ctx, by_pass, q, make_task(ctx, p, dout - (size_t)(jb.offset + 1) * half, half, dsrc, p.src_pitch, /*copy_kept=*/0));
+            }
+        }
+        if (status != SN_OK) break;
+        PL_CUDA(flush_segments(up_segs, cudaMemcpyHostToDevice, h2d_), "H2D copy");
+        // The task array rides the upload stream too: a small copy on the compute stream would queue on the
+        // same DMA engine behind the NEXT chunks' bulk uploads and hold this chunk's kernels back.
+        PL_CUDA(upload_tasks(by_pass, static_cast<sn::PlaneTask*>(s.tasks_host.p), static_cast<sn::PlaneTask*>(s.tasks.p), h2d_), "task upload");
+        // persistent pool: every chunk's kernels on ONE stream, so that frames run in submission order across chunks
+        const cudaStream_t compute = ctx->persistent ? slots_[0].compute : s.compute;
+        PL_CUDA(cudaEventRecord(s.h2d_done, h2d_), "event");
+        PL_CUDA(cudaStreamWaitEvent(compute, s.h2d_done, 0), "event");
+
+        // ---- kernels ----
+        if (g_trace) cudaEventRecord(s.t_k0, compute);
+        PL_CUDA(launch_passes(ctx, by_pass, static_cast<sn::PlaneTask*>(s.tasks.p), compute), "kernel launch");
+        PL_CUDA(cudaEventRecord(s.kernels_done, compute), "event");
+        PL_CUDA(cudaStreamWaitEvent(d2h_, s.kernels_done, 0), "event");
+
+        // ---- download of the interpolated rows ----
+        if (g_trace) cudaEventRecord(s.t_d2h0, d2h_);
+        for (size_t k = c.first; k < c.last && status == SN_OK; ++k) {
+            for (Pass& p : frames[k].passes) {
+                if (p.n < 2) continue;
+                const sn_plane_job& jb = *p.job;
+                const size_t row = (size_t)p.W * sb;
+                char* const dout = dplanes + out_base + p.out_off;
+                if (p.down == Pass::STAGED) {
+                    add_segment(down_segs, static_cast<char*>(s.stage_out.p) + p.stage_out_off, dout, p.out_pitch * (size_t)(p.n - 1), -1);
+                    d2h_bytes += p.out_pitch * (size_t)(p.n - 1);
+                } else {
+                    PL_CUDA(flush_segments(down_segs, cudaMemcpyDeviceToHost, d2h_), "D2H copy");
+                    PL_CUDA(cudaMemcpy2DAsync(static_cast<char*>(jb.dst) + (ptrdiff_t)(jb.offset + 1) * jb.dst_pitch, 2 * (size_t)jb.dst_pitch, dout, p.out_pitch,
+                                              row, (size_t)(p.n - 1), cudaMemcpyDeviceToHost, d2h_), "D2H copy");
+                    d2h_bytes += row * (size_t)(p.n - 1);
+                }
+            }
+        }
+        if (status != SN_OK) break;
+        PL_CUDA(flush_segments(down_segs, cudaMemcpyDeviceToHost, d2h_), "D2H copy");
+        PL_CUDA(cudaEventRecord(s.d2h_done, d2h_), "event");
+        s.busy = true;
+        s.chunk = c;
+        {
+            std::lock_guard<std::mutex> lk(ctx->stats_mu);
+            ctx->stats.h2d_bytes += h2d_bytes;
+            ctx->stats.d2h_bytes += d2h_bytes;
+            ctx->stats.host_copy_bytes += host_bytes;
+        }
+    } while (0);
+
+    if (status != SN_OK) {
+        // leave nothing of this chunk in flight that reads or writes user memory
+        cudaStreamSynchronize(h2d_);
+        cudaStreamSynchronize(ctx->persistent ? slots_[0].compute : s.compute);
+        cudaStreamSynchronize(d2h_);
+        cudaGetLastError();
+    }
+    return status;
+}
+
+// Wait for the chunk's download and scatter the interpolated rows of pageable destinations out of the staging buffer.
+int Pipeline::finish_slot(Slot& s, std::string& err)
+{
+    if (!s.busy) return SN_OK;
+    s.busy = false;
+    const cudaError_t e = cudaEventSynchronize(s.d2h_done);
+    if (e != cudaSuccess) { err = std::string("waiting for the download: ") + cudaGetErrorString(e); cudaGetLastError(); return SN_ERR_CUDA; }
+    if (g_trace) {
+        float t[6] = {};
+        cudaEventElapsedTime(&t[0], trace_base_, s.t_h2d0); cudaEventElapsedTime(&t[1], trace_base_, s.h2d_done);
+        cudaEventElapsedTime(&t[2], trace_base_, s.t_k0); cudaEventElapsedTime(&t[3], trace_base_, s.kernels_done);
+        cudaEventElapsedTime(&t[4], trace_base_, s.t_d2h0); cudaEventElapsedTime(&t[5], trace_base_, s.d2h_done);
+        fprintf(stderr, "[sangnom] device %d chunk of %3zu frames: h2d %7.2f..%7.2f  kernels %7.2f..%7.2f  d2h %7.2f..%7.2f ms\n",
+                device_, s.chunk.last - s.chunk.first, t[0], t[1], t[2], t[3], t[4], t[5]);
+    }
+    const int sb = ctx_->sample_bytes;
+    std::vector<RowCopy> copies;
+    uint64_t host_bytes = 0;
+    std::vector<FramePlan>& frames = s.chunk.batch->frames;
+    for (size_t k = s.chunk.first; k < s.chunk.last; ++k)
+        for (Pass& p : frames[k].passes) {
+            if (p.down != Pass::STAGED || p.n < 2) continue;
+            const sn_plane_job& jb = *p.job;
+            copies.push_back(RowCopy{ static_cast<char*>(jb.dst) + (ptrdiff_t)(jb.offset + 1) * jb.dst_pitch, static_cast<const char*>(s.stage_out.p) + p.stage_out_off,
+                                      2 * jb.dst_pitch, (ptrdiff_t)p.out_pitch, (size_t)p.W * sb, p.n - 1 });
+            host_bytes += (uint64_t)p.W * sb * (p.n - 1);
+        }
+    pool_.run(copies);
+    if (host_bytes) {
+        std::lock_guard<std::mutex> lk(ctx_->stats_mu);
+        ctx_->stats.host_copy_bytes += host_bytes;
+    }
+    return SN_OK;
+}
+
+}  // namespace sn_host

@@ -5,7 +5,8 @@
 //            takes its 16-byte window, builds the +-3 byte shifts, the 3-tap values of the row (once per
 //            row, reused for two pairs), the nine raw costs P[r+1] four pixels per VABSDIFF4, widens them
 //            to 16-bit lanes and publishes L = B[r-1] + P[r] + P[r+1] to a double-buffered shared row;
-//   barrier  one per row (block barrier, or the cluster barrier when the plane is split over blocks);
+//   barrier  one block barrier per row; when the plane is split over the blocks of a cluster, the two edge threads
+//            of a block also exchange their halo with the neighbour blocks (sangnom_cluster.cuh) - no cluster barrier;
 //   phase B  per cost: 7-tap sum of L two columns per op, key = (sum & 0x0FF0) | rank in both lanes
 //            ((B << 4) | tie-break rank; B = wrap8(sum >> 4)), running term M = P[r+1] + (key >> 4) in ONE
 //            LEA.HI - the rank nibble of the upper lane that this shifts into the lower lane is a per-cost
@@ -226,13 +227,14 @@ __device__ __forceinline__ uint2 load8_guarded(const uint8_t* __restrict__ row, 
 //   ring  [kRing][ring_stride]  staged kept rows, row position p at offset p - seg_x0 + kRingPad
 //   t3    [kT3Ring][T] uint4    3-tap bytes of the kept rows (thread-private slots)
 //   mbar  [kRing]               one mbarrier per ring slot
+//   halo  [2 sides][2 parities] barriers the neighbour blocks' halo stores complete on (cluster launches)
 //   task                        this block's PlaneTask
 inline __host__ __device__ int ring_stride(int seg_cols) { return (seg_cols + 2 * kRingPad + 15) & ~15; }
 inline __host__ __device__ size_t l_bytes(int seg_cols) { return (size_t)2 * (seg_cols / kCols + 2) * kLEntry * sizeof(uint2); }
 inline size_t smem_bytes(int seg_cols)
 {
     return ((l_bytes(seg_cols) + 15) & ~(size_t)15) + (size_t)kRing * ring_stride(seg_cols) + (size_t)kT3Ring * (seg_cols / kCols) * sizeof(uint4) +
-           kRing * sizeof(stage::Mbar) + ((sizeof(PlaneTask) + 15) & ~(size_t)15);
+           kRing * sizeof(stage::Mbar) + 4 * 16 /* halo barriers */ + ((sizeof(PlaneTask) + 15) & ~(size_t)15);
 }
 
 // kSpare: the launch brings spare threads for planes narrower than the pool (see the thread -> column map below); planes
@@ -255,13 +257,16 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     stage::Mbar* const mbar = reinterpret_cast<stage::Mbar*>(t3ring + (size_t)kT3Ring * T);
     // the task lives in shared memory: its rarely used fields (cost-state regions, pitches) are re-read where needed
     // instead of occupying registers for the whole sweep
+    // halo barriers, 16 bytes apart: [side 0 = left, 1 = right][row parity]
+    unsigned char* const halo_raw = reinterpret_cast<unsigned char*>(mbar + kRing);
+    auto halo_bar = [&](int side, int par) -> cl::HaloBar* { return reinterpret_cast<cl::HaloBar*>(halo_raw + (side * 2 + par) * 16); };
     {
-        uint32_t* const dst = reinterpret_cast<uint32_t*>(mbar + kRing);
+        uint32_t* const dst = reinterpret_cast<uint32_t*>(halo_raw + 4 * 16);
         const uint32_t* const from = reinterpret_cast<const uint32_t*>(tasks + blockIdx.x / G);
         for (unsigned k = threadIdx.x; k < sizeof(PlaneTask) / 4; k += blockDim.x) dst[k] = from[k];
         __syncthreads();
     }
-    const PlaneTask& t = *reinterpret_cast<const PlaneTask*>(mbar + kRing);
+    const PlaneTask& t = *reinterpret_cast<const PlaneTask*>(halo_raw + 4 * 16);
 
     const int W = t.width, n = t.kept_rows, R = t.sweep_rows;
     const int seg_x0 = (int)crank * seg_cols;
@@ -401,9 +406,9 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
             tap3_row<kSat>(Ta, ta);
             t3_put(0, ta);
             // border row without a neighbour pair (reference GetFrame :380-391) and, for a one-pair-less plane, the kept row
-            if (t.offset != 0) store8(0, make_uint2(wa[1], wa[2]));
+            if (t.offset != 0 && !t.no_border) store8(0, make_uint2(wa[1], wa[2]));
             if (n == 1) {
-                if (t.offset == 0) store8(t.height - 1, make_uint2(wa[1], wa[2]));
+                if (t.offset == 0 && !t.no_border) store8(t.height - 1, make_uint2(wa[1], wa[2]));
                 if (t.copy_kept) store8(t.offset, make_uint2(wa[1], wa[2]));
             } else {
                 await_row(1);
@@ -431,8 +436,15 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
 #endif
     uint32_t sp[kNumCost][2];
     if (!warp_full) stale_costs(2, sp);
-    // all blocks of a cluster run before the first DSMEM store
-    if constexpr (kClustered) cl::sync_all();
+    // all blocks of a cluster run, with their halo barriers initialised, before the first DSMEM store
+    if constexpr (kClustered) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) cl::halo_init(halo_bar(b >> 1, b & 1));
+            cl::halo_fence_init();
+        }
+        cl::sync_all();
+    }
 
     const uint32_t tkey = (uint32_t)min(t.thr_i + 1, 4095) * 0x00100010u;    // (thr+1) << 4 in both lanes
     // Dependency cone (sangnom_plan.h): at pool row r only columns < cone - 3r can still reach a picture sample of this
@@ -499,15 +511,16 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
         }
         // the two edge threads of the segment supply what lies beyond it: the clamp of the recursion at pool columns 0
         // and S-1 (reference :144-152), or - plane split over a cluster - the neighbour block's halo (DSMEM)
+        // (the block right of mine is there as long as its first column is inside the cone; once it has left there is
+        // nothing to send it and nothing to wait for)
+        const bool right_block = kClustered && seg_last && !plane_last && 3 * r + seg_x0 + seg_cols < t.cone;
+        [[maybe_unused]] const unsigned halo_parity = (unsigned)((r - 1) >> 1) & 1u;        // barrier [side][r & 1] completes its ((r-1)/2)-th phase at row r
         if (seg_first) {
 #pragma unroll
             for (int i = 0; i < kNumCost; ++i) {
                 const uint2 Lxy = Lrow[2 * i];
                 if (plane_first) { const uint32_t e = (Lxy.x & 0xFFFFu) * 0x00010001u; Lrow[2 * i + 1 - kLEntry] = make_uint2(e, e); }
-                else {
-                    cl::store_remote(&Lrow[2 * i + T * kLEntry].x, crank - 1, Lxy.x);
-                    cl::store_remote(&Lrow[2 * i + T * kLEntry].y, crank - 1, Lxy.y);
-                }
+                else cl::store_remote_tx(&Lrow[2 * i + T * kLEntry], crank - 1, Lxy, halo_bar(1, r & 1));          // the left block's right halo
             }
         }
         if (seg_last) {
@@ -515,14 +528,14 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
             for (int i = 0; i < kNumCost; ++i) {
                 const uint2 Lzw = Lrow[2 * i + 1];
                 if (plane_last) { const uint32_t e = (Lzw.y >> 16) * 0x00010001u; Lrow[2 * i + kLEntry] = make_uint2(e, e); }
-                else if (3 * r + seg_x0 + seg_cols < t.cone) {              // the block right of mine is still there: once its first column is outside
-                                                                            // the cone it has exited, and DSMEM of an exited block must not be written
-                    cl::store_remote(&Lrow[2 * i + 1 - T * kLEntry].x, crank + 1, Lzw.x);
-                    cl::store_remote(&Lrow[2 * i + 1 - T * kLEntry].y, crank + 1, Lzw.y);
-                }
+                else if (right_block) cl::store_remote_tx(&Lrow[2 * i + 1 - T * kLEntry], crank + 1, Lzw, halo_bar(0, r & 1));   // the right block's left halo
             }
         }
-        if constexpr (kClustered) cl::sync_all(); else __syncthreads();
+        __syncthreads();
+        if constexpr (kClustered) {                         // the one thread that reads a neighbour block's halo waits for it
+            if (seg_first && !plane_first) cl::halo_wait(halo_bar(0, r & 1), halo_parity, kNumCost * 8u);
+            if (right_block) cl::halo_wait(halo_bar(1, r & 1), halo_parity, kNumCost * 8u);
+        }
         if constexpr (!kFull) stale_costs(r + 2, sp);       // next row's handed-over state: in flight during phase B
 
         // ---- per cost: 7-tap sum, key = (B << 4) | rank, M = P[r+1] + B (+ leak), min over the keys ----
@@ -584,7 +597,7 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
             store8(y + 1, px);
             if (t.copy_kept) store8(y, make_uint2(wa[1], wa[2]));
             if (!kPair) {                                                   // K[r] is the last kept row
-                if (t.offset == 0) store8(t.height - 1, make_uint2(wb[1], wb[2]));
+                if (t.offset == 0 && !t.no_border) store8(t.height - 1, make_uint2(wb[1], wb[2]));
                 if (t.copy_kept) store8(y + 2, make_uint2(wb[1], wb[2]));
             }
         }

@@ -9,7 +9,8 @@
 //            (K[r], K[r+1]) and publishes L = M + P[r+1] to a double-buffered shared row. The L row is entry-major:
 //            the nine 16-byte vectors of a thread are 144 bytes apart from the next thread's, so every access is a
 //            conflict-free 128-bit one and every per-cost offset an immediate;
-//   barrier  one per row (block barrier, or the cluster barrier when the plane is split over blocks);
+//   barrier  one block barrier per row; when the plane is split over the blocks of a cluster, the two edge threads
+//            of a block also exchange their halo with the neighbour blocks (sangnom_cluster.cuh) - no cluster barrier;
 //   phase B  per cost: three 128-bit reads (left neighbour, own, right neighbour), the 7-tap sum (integers: sliding,
 //            1.5 adds per column; fp32: the reference's left-to-right order, each add rounded), /16, narrow to T,
 //            min key (integers: (B << 4) | rank with the threshold as a tenth key; fp32: strict '<' in tie order),
@@ -140,13 +141,14 @@ __device__ __forceinline__ typename Vec4<T>::type load4_guarded(const T* __restr
 //   ring  [kRing][ring_stride]   staged kept rows, row position p at byte offset (p - seg_x0) * sizeof(T) + kRingPadBytes
 //   t3    [kT3Ring][2][seg_cols] the two 3-tap values of every pixel of a kept row, as samples (f, then b)
 //   mbar  [kRing]                one mbarrier per ring slot
+//   halo  [2 sides][2 parities]  barriers the neighbour blocks' halo stores complete on (cluster launches)
 //   task                         this block's PlaneTask
 template <typename T> inline __host__ __device__ int ring_stride(int seg_cols) { return (seg_cols * (int)sizeof(T) + 2 * kRingPadBytes + 15) & ~15; }
 inline __host__ __device__ size_t l_bytes(int seg_cols) { return (size_t)2 * (seg_cols / kCols + 2) * kLEntry * sizeof(uint4); }
 template <typename T> inline size_t smem_bytes(int seg_cols)
 {
     return l_bytes(seg_cols) + (size_t)kRing * ring_stride<T>(seg_cols) + (size_t)kT3Ring * 2 * seg_cols * sizeof(T) +
-           kRing * sizeof(stage::Mbar) + ((sizeof(PlaneTask) + 15) & ~(size_t)15);
+           kRing * sizeof(stage::Mbar) + 4 * 16 /* halo barriers */ + ((sizeof(PlaneTask) + 15) & ~(size_t)15);
 }
 
 // kSpare: the launch brings spare threads for planes narrower than the pool (see the thread -> column map below).
@@ -169,14 +171,17 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
     unsigned char* const ring = smem_raw + l_bytes(seg_cols);
     T* const t3ring = reinterpret_cast<T*>(ring + (size_t)kRing * rstride);
     stage::Mbar* const mbar = reinterpret_cast<stage::Mbar*>(t3ring + (size_t)kT3Ring * 2 * seg_cols);
+    // halo barriers, 16 bytes apart: [side 0 = left, 1 = right][row parity]
+    unsigned char* const halo_raw = reinterpret_cast<unsigned char*>(mbar + kRing);
+    auto halo_bar = [&](int side, int par) -> cl::HaloBar* { return reinterpret_cast<cl::HaloBar*>(halo_raw + (side * 2 + par) * 16); };
     // the task lives in shared memory: its rarely used fields are re-read where needed instead of occupying registers
     {
-        uint32_t* const dst = reinterpret_cast<uint32_t*>(mbar + kRing);
+        uint32_t* const dst = reinterpret_cast<uint32_t*>(halo_raw + 4 * 16);
         const uint32_t* const from = reinterpret_cast<const uint32_t*>(tasks + blockIdx.x / G);
         for (unsigned k = threadIdx.x; k < sizeof(PlaneTask) / 4; k += blockDim.x) dst[k] = from[k];
         __syncthreads();
     }
-    const PlaneTask& t = *reinterpret_cast<const PlaneTask*>(mbar + kRing);
+    const PlaneTask& t = *reinterpret_cast<const PlaneTask*>(halo_raw + 4 * 16);
 
     const int W = t.width, n = t.kept_rows, R = t.sweep_rows;
     const int seg_x0 = (int)crank * seg_cols;
@@ -343,9 +348,9 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
             t3_put(0, ta);
             const I own[4] = { wa[4], wa[5], wa[6], wa[7] };
             // border row without a neighbour pair (reference GetFrame :380-391) and, for a one-pair-less plane, the kept row
-            if (t.offset != 0) store4(0, pack4(own, T()));
+            if (t.offset != 0 && !t.no_border) store4(0, pack4(own, T()));
             if (n == 1) {
-                if (t.offset == 0) store4(t.height - 1, pack4(own, T()));
+                if (t.offset == 0 && !t.no_border) store4(t.height - 1, pack4(own, T()));
                 if (t.copy_kept) store4(t.offset, pack4(own, T()));
             } else {
                 await_row(1, 0u);
@@ -375,10 +380,18 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
 #endif
     I sp[kNumCost][kCols];
     if (!warp_full) stale_costs(2, sp);
-    // all blocks of a cluster run before the first DSMEM store
-    if constexpr (kClustered) cl::sync_all();
+    // all blocks of a cluster run, with their halo barriers initialised, before the first DSMEM store
+    if constexpr (kClustered) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) cl::halo_init(halo_bar(b >> 1, b & 1));
+            cl::halo_fence_init();
+        }
+        cl::sync_all();
+    }
 
     const int tkey = (int)min((long long)t.thr_i + 1, 0x7FFFFFFLL) << 4;      // (thr+1) << 4: "every cost above the threshold"
+    const unsigned keymask = g.key_mask;                            // kMask << 4, kept in a register so that (sum & mask) | rank is one LOP3
     const float thr_f = t.thr_f;
     // dependency cone (sangnom_plan.h): the last pool row my warp still has anything to do at
     const int r_last = min(R, (t.cone - 1 - (seg_x0 + wfirst * kCols)) / 3);
@@ -439,12 +452,16 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
         // the two edge threads of the segment supply what lies beyond it: the clamp of the recursion at pool columns 0
         // and S-1 (reference :144-152 clamps at the pool stride), or - plane split over a cluster - the neighbour
         // block's halo (DSMEM). The neighbour reads columns 1..3 of its left halo entry and 0..2 of its right one.
+        // (the block right of mine is there as long as its first column is inside the cone; once it has left there is
+        // nothing to send it and nothing to wait for)
+        const bool right_block = kClustered && seg_last && !plane_last && 3 * r + seg_x0 + seg_cols < t.cone;
+        [[maybe_unused]] const unsigned halo_parity = (unsigned)((r - 1) >> 1) & 1u;        // barrier [side][r & 1] completes its ((r-1)/2)-th phase at row r
         if (seg_first) {
 #pragma unroll
             for (int i = 0; i < kNumCost; ++i) {
                 const uint4 Lv = Lrow[i];
                 if (plane_first) Lrow[i - kLEntry] = make_uint4(Lv.x, Lv.x, Lv.x, Lv.x);
-                else cl::store_remote4(&Lrow[i + Tn * kLEntry], crank - 1, Lv);
+                else cl::store_remote_tx(&Lrow[i + Tn * kLEntry], crank - 1, Lv, halo_bar(1, r & 1));      // the left block's right halo
             }
         }
         if (seg_last) {
@@ -452,10 +469,14 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
             for (int i = 0; i < kNumCost; ++i) {
                 const uint4 Lv = Lrow[i];
                 if (plane_last) Lrow[i + kLEntry] = make_uint4(Lv.w, Lv.w, Lv.w, Lv.w);
-                else if (3 * r + seg_x0 + seg_cols < t.cone) cl::store_remote4(&Lrow[i - Tn * kLEntry], crank + 1, Lv);     // not into a block that has left (cone)
+                else if (right_block) cl::store_remote_tx(&Lrow[i - Tn * kLEntry], crank + 1, Lv, halo_bar(0, r & 1));    // the right block's left halo
             }
         }
-        if constexpr (kClustered) cl::sync_all(); else __syncthreads();
+        __syncthreads();
+        if constexpr (kClustered) {                         // the one thread that reads a neighbour block's halo waits for it
+            if (seg_first && !plane_first) cl::halo_wait(halo_bar(0, r & 1), halo_parity, kNumCost * 16u);
+            if (right_block) cl::halo_wait(halo_bar(1, r & 1), halo_parity, kNumCost * 16u);
+        }
         if constexpr (!kFull) stale_costs(r + 2, sp);       // next row's handed-over state: in flight during phase B
 
         // ---- per cost: 7-tap sum, B = narrowT(sum / 16), min key, M = P[r+1] + B ----
@@ -464,7 +485,7 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
         int frank[kCols];
 #pragma unroll
         for (int c = 0; c < kCols; ++c) { kmin[c] = tkey; fmin[c] = 0.f; frank[c] = 0; }
-        int held[kCols];
+        [[maybe_unused]] int held[kCols];
         T* outp = out.p;
         // Costs are visited 0, 1, .. 8 for integers (the tie order lives in the keys); for fp32 in the reference's tie
         // order 4,5,3,6,2,7,1,8,0, so that a strict '<' leaves the first of several equal minima as the winner
@@ -498,7 +519,7 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
                 for (int c = 0; c < kCols; ++c) {
                     if (c > 0) s += Lw[c + 7] - Lw[c];
                     // narrowT(s / 16) << 4 | rank: wrapped (:152), or clamped for the SSE2 flavour (SangNom2_SSE2.cpp:807)
-                    const unsigned kept = kSat ? min((unsigned)s, ((unsigned)Flavour<T>::kMask << 4) | 15u) & ~15u : (unsigned)s & ((unsigned)Flavour<T>::kMask << 4);
+                    const unsigned kept = kSat ? min((unsigned)s, keymask | 15u) & keymask : (unsigned)s & keymask;
                     const int key = (int)(kept | (unsigned)rank_of(i));
                     B4[c] = key >> 4;
                     if (k & 1) kmin[c] = (int)__vimin3_u32((unsigned)kmin[c], (unsigned)held[c], (unsigned)key);
@@ -522,30 +543,35 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
             t3_get(ph3_prev, tu);
             t3_get(ph3, td);
             I px[kCols];
+            // the winning direction's operands, fetched by index; a warp with a picture edge in it clamps the taps
+            // (loadPixel :25-34) - a warp-uniform choice made once per row, not per pixel
+            auto interpolate = [&](auto clamped) {
 #pragma unroll
-            for (int c = 0; c < kCols; ++c) {
-                int rank;
-                if constexpr (kFloat) rank = fmin[c] > thr_f ? 0 : frank[c];
-                else rank = kmin[c] & 15;
-                const int d3 = tap_index(rank);                             // d + 3
-                I a, b;
-                if (warp_edge) {                                            // a picture edge in this warp: clamp the taps (loadPixel :25-34)
-                    const int xa = min(max(x0 + c + d3 - 3, 0), W - 1), xb = min(max(x0 + c + 3 - d3, 0), W - 1);
-                    a = (I)(up + 3 - x0)[xa];
-                    b = (I)(dn - 3 - x0)[xb];
-                } else {
-                    a = (I)up[c + d3];
-                    b = (I)dn[c - d3];
+                for (int c = 0; c < kCols; ++c) {
+                    int rank;
+                    if constexpr (kFloat) rank = fmin[c] > thr_f ? 0 : frank[c];
+                    else rank = kmin[c] & 15;
+                    const int d3 = tap_index(rank);                         // d + 3
+                    I a, b;
+                    if constexpr (decltype(clamped)::value) {
+                        const int xa = min(max(x0 + c + d3 - 3, 0), W - 1), xb = min(max(x0 + c + 3 - d3, 0), W - 1);
+                        a = (I)(up + 3 - x0)[xa];
+                        b = (I)(dn - 3 - x0)[xb];
+                    } else {
+                        a = (I)up[c + d3];
+                        b = (I)dn[c - d3];
+                    }
+                    if (rank == 1) { a = tu.b[c]; b = td.f[c]; }
+                    if (rank == 2) { a = tu.f[c]; b = td.b[c]; }
+                    px[c] = mean2(a, b);
                 }
-                if (rank == 1) { a = tu.b[c]; b = td.f[c]; }
-                if (rank == 2) { a = tu.f[c]; b = td.b[c]; }
-                px[c] = mean2(a, b);
-            }
+            };
+            if (warp_edge) interpolate(std::true_type{}); else interpolate(std::false_type{});
             const int y = t.offset + 2 * (r - 1);
             store4(y + 1, pack4(px, T()));
             if (t.copy_kept) store4(y, own4(sm1));
             if (!kPair) {                                                   // K[r] is the last kept row
-                if (t.offset == 0) store4(t.height - 1, own4(s0));
+                if (t.offset == 0 && !t.no_border) store4(t.height - 1, own4(s0));
                 if (t.copy_kept) store4(y + 2, own4(s0));
             }
         }

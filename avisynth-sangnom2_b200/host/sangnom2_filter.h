@@ -7,8 +7,10 @@
 // avisynth.h, so it builds against the SDK header as well as against the tests' stand-in tests/fakehost_src/avs_stub/avisynth.h.
 #pragma once
 
+#include <cstdint>
 #include <map>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "avisynth.h"
@@ -39,6 +41,16 @@ class SangNom2 : public GenericVideoFilter {
         sn_ticket ticket = 0;
         std::vector<PVideoFrame> srcs, dsts;   // keep the frame buffers alive until the batch is waited for
     } pending_;
+
+    // Frame buffers the host keeps recycling (AviSynth+'s frame registry hands the same VideoFrameBuffers out again
+    // and again) are pinned for DMA the second time they are seen, so that their planes travel without the staging
+    // copies of pageable memory; least recently used ones are unpinned when the budget is exceeded. Only ever touched
+    // while no batch is in flight. SANGNOM_B200_PIN_MB=0 switches it off (see INTEGRATION.md for when to do that).
+    struct PinEntry { size_t bytes = 0; int seen = 0; uint64_t last_use = 0; bool pinned = false; };
+    std::unordered_map<const void*, PinEntry> pins_;
+    size_t pinned_bytes_ = 0, pin_budget_ = 0;
+    uint64_t pin_clock_ = 0;
+    void note_frame_buffer(const PVideoFrame& f);
 
     int field_offset(int n);
     void start_batch(int first, int count, IScriptEnvironment* env);

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -51,6 +52,19 @@ SangNom2::SangNom2(PClip _child, int order, int aa, int aac, int threads, bool d
     sn_config cfg{};
     cfg.abi_version = SANGNOM_CUDA_ABI_VERSION;
     cfg.device = env_int("SANGNOM_B200_DEVICE", 0, 0, 1023);
+    // SANGNOM_B200_DEVICES=all | 0,2,3: one pipeline per listed GPU behind this one filter instance, chunks of frames
+    // dealt round-robin (what the reference gets from MT_MULTI_INSTANCE clones, SangNom2.h:63-66)
+    if (const char* v = std::getenv("SANGNOM_B200_DEVICES")) {
+        if (std::strcmp(v, "all") == 0) cfg.device = SN_DEVICE_ALL;
+        else
+            for (const char* p = v; *p;) {
+                char* end = nullptr;
+                const long d = std::strtol(p, &end, 10);
+                if (end == p) break;
+                if (d >= 0 && d < 64) cfg.device_mask |= 1ull << d;
+                p = *end == ',' ? end + 1 : end;
+            }
+    }
     cfg.sample_type = sample_bytes_;
     cfg.pool_width = vi.width;       // pool geometry comes from the OUTPUT luma size (:287-288)
     cfg.pool_height = vi.height;
@@ -67,6 +81,7 @@ SangNom2::SangNom2(PClip _child, int order, int aa, int aac, int threads, bool d
     if (opt == 1 || (opt < 0 && (env->GetCPUFlags() & CPUF_SSE2))) cfg.flags |= SN_FLAG_SATURATE;
     // SANGNOM_B200_PREFETCH=0: no speculative next batch (every child frame is requested only when it is needed)
     prefetch_ = env_int("SANGNOM_B200_PREFETCH", 1, 0, 1) != 0;
+    pin_budget_ = (size_t)env_int("SANGNOM_B200_PIN_MB", 2048, 0, 1 << 20) << 20;
     if (sangnom_cuda_create(&cfg, &ctx_) != SN_OK)
         env->ThrowError("SangNom2: %s", sangnom_cuda_last_error(nullptr));
 }
@@ -74,9 +89,42 @@ SangNom2::SangNom2(PClip _child, int order, int aa, int aac, int threads, bool d
 SangNom2::~SangNom2()
 {
     if (pending_.active) sangnom_cuda_wait(ctx_, pending_.ticket);     // nothing may still write into the frames
+    for (auto& kv : pins_)
+        if (kv.second.pinned) sangnom_cuda_host_unpin(ctx_, const_cast<void*>(kv.first));
+    pins_.clear();
     pending_ = Pending{};
     ready_.clear();
     sangnom_cuda_destroy(ctx_);
+}
+
+void SangNom2::note_frame_buffer(const PVideoFrame& f)
+{
+    if (pin_budget_ == 0) return;
+    VideoFrameBuffer* const vfb = f->GetFrameBuffer();
+    const void* const base = vfb->GetReadPtr();
+    const size_t bytes = (size_t)vfb->GetDataSize();
+    if (!base || bytes == 0 || bytes > pin_budget_) return;
+    PinEntry& e = pins_[base];
+    if (e.bytes != bytes) {                                 // a different buffer at an address seen before
+        if (e.pinned) { sangnom_cuda_host_unpin(ctx_, const_cast<void*>(base)); pinned_bytes_ -= e.bytes; }
+        e = PinEntry{};
+        e.bytes = bytes;
+    }
+    e.last_use = ++pin_clock_;
+    if (e.pinned || ++e.seen < 2) return;                   // pinned already, or seen for the first time: may be a one-off
+    while (pinned_bytes_ + bytes > pin_budget_) {           // make room: unpin the least recently used buffer
+        auto lru = pins_.end();
+        for (auto it = pins_.begin(); it != pins_.end(); ++it)
+            if (it->second.pinned && (lru == pins_.end() || it->second.last_use < lru->second.last_use)) lru = it;
+        if (lru == pins_.end()) return;
+        sangnom_cuda_host_unpin(ctx_, const_cast<void*>(lru->first));
+        pinned_bytes_ -= lru->second.bytes;
+        pins_.erase(lru);
+    }
+    if (sangnom_cuda_host_pin(ctx_, const_cast<void*>(base), bytes) == SN_OK) { e.pinned = true; pinned_bytes_ += bytes; }
+    else e.seen = -1000;                                    // the driver refused: leave this one pageable
+    if (pins_.size() > 4096)                                // forget stale one-off entries
+        for (auto it = pins_.begin(); it != pins_.end();) it = (!it->second.pinned && it->second.last_use + 2048 < pin_clock_) ? pins_.erase(it) : std::next(it);
 }
 
 // 0 keeps the top field (rows 0,2,..), 1 the bottom field (reference :336-341).
@@ -102,6 +150,8 @@ void SangNom2::start_batch(int first, int count, IScriptEnvironment* env)
         const int offset = field_offset(n);
         srcs[k] = child->GetFrame(n, env);
         dsts[k] = has_at_least_v8_ ? env->NewVideoFrameP(vi, &srcs[k]) : env->NewVideoFrame(vi);
+        note_frame_buffer(srcs[k]);
+        note_frame_buffer(dsts[k]);
         for (int i = 0; i < plane_count_; ++i) {
             const int plane = kPlaneIds[i];
             sn_plane_job jb{};

@@ -16,7 +16,8 @@ CUDA_LIB = os.path.join(_PKG_DIR, "libsangnom_cuda.so")
 
 SN_OK, SN_ERR_INVALID, SN_ERR_CUDA, SN_ERR_UNSUPPORTED, SN_ERR_NOMEM = range(5)
 MODE_COPY, MODE_FIELD, MODE_DH, MODE_INPLACE = range(4)
-ABI_VERSION = 1
+ABI_VERSION = 2
+DEVICE_ALL = -1
 FLAG_PERSISTENT_POOL = 1
 FLAG_SATURATE = 2
 
@@ -27,13 +28,15 @@ EXPORTS = [
     "sangnom_cuda_host_free", "sangnom_cuda_last_error", "sangnom_cuda_submit", "sangnom_cuda_wait",
     "sangnom_cuda_chain_create", "sangnom_cuda_chain_destroy", "sangnom_cuda_chain_process", "sangnom_cuda_chain_get_stats",
     "sangnom_cuda_chain_last_error", "sangnom_cuda_turn_planes_device",
+    "sangnom_cuda_host_pin", "sangnom_cuda_host_unpin", "sangnom_cuda_device_count",
 ]
 TURN_TRANSPOSE, TURN_RIGHT_LEFT, TURN_LEFT_RIGHT = range(3)
 
 
 class SnConfig(C.Structure):
     _fields_ = [("abi_version", C.c_int), ("device", C.c_int), ("sample_type", C.c_int), ("pool_width", C.c_int),
-                ("pool_height", C.c_int), ("max_frames_in_flight", C.c_int), ("flags", C.c_int)]
+                ("pool_height", C.c_int), ("max_frames_in_flight", C.c_int), ("flags", C.c_int),
+                ("device_mask", C.c_ulonglong), ("copy_threads", C.c_int)]
 
 
 class SnPlaneJob(C.Structure):
@@ -69,7 +72,7 @@ class SnLimits(C.Structure):
 
 class SnStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("planes_processed", C.c_uint64), ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64), ("frames", C.c_uint64)]
+                ("d2h_bytes", C.c_uint64), ("frames", C.c_uint64), ("host_copy_bytes", C.c_uint64)]
 
 
 class SangNomCudaError(RuntimeError):
@@ -130,6 +133,12 @@ def load():
     L.sangnom_cuda_host_free.argtypes = [C.c_void_p]
     L.sangnom_cuda_last_error.restype = C.c_char_p
     L.sangnom_cuda_last_error.argtypes = [C.c_void_p]
+    L.sangnom_cuda_host_pin.restype = C.c_int
+    L.sangnom_cuda_host_pin.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.sangnom_cuda_host_unpin.restype = C.c_int
+    L.sangnom_cuda_host_unpin.argtypes = [C.c_void_p, C.c_void_p]
+    L.sangnom_cuda_device_count.restype = C.c_int
+    L.sangnom_cuda_device_count.argtypes = [C.c_void_p]
     if L.sangnom_cuda_abi_version() != ABI_VERSION:
         raise RuntimeError("libsangnom_cuda ABI version mismatch")
     _lib = L
@@ -198,11 +207,17 @@ def make_job(src_ptr, src_pitch, dst_ptr, dst_pitch, width, dst_height, offset, 
 
 
 class Context:
-    """sn_ctx wrapper. pool_width/pool_height are the OUTPUT luma dims (after dh)."""
+    """sn_ctx wrapper. pool_width/pool_height are the OUTPUT luma dims (after dh).
+    device: ordinal, DEVICE_ALL, or a list of ordinals (one host pipeline per device behind one context)."""
 
-    def __init__(self, sample_bytes, pool_width, pool_height, device=0, max_frames_in_flight=0, flags=0):
+    def __init__(self, sample_bytes, pool_width, pool_height, device=0, max_frames_in_flight=0, flags=0, copy_threads=0):
         L = load()
-        cfg = SnConfig(ABI_VERSION, device, sample_bytes, pool_width, pool_height, max_frames_in_flight, flags)
+        mask = 0
+        if isinstance(device, (list, tuple)):
+            for d in device:
+                mask |= 1 << int(d)
+            device = int(device[0])
+        cfg = SnConfig(ABI_VERSION, device, sample_bytes, pool_width, pool_height, max_frames_in_flight, flags, mask, copy_threads)
         h = C.c_void_p()
         rc = L.sangnom_cuda_create(C.byref(cfg), C.byref(h))
         if rc != SN_OK:
@@ -254,6 +269,16 @@ class Context:
 
     def synchronize(self):
         self._check(load().sangnom_cuda_synchronize(self._h))
+
+    def device_count(self):
+        return int(load().sangnom_cuda_device_count(self._h))
+
+    def host_pin(self, array):
+        """Pin the memory of a (long-lived, contiguous) numpy array the caller owns; planes inside it then travel by DMA."""
+        self._check(load().sangnom_cuda_host_pin(self._h, array.ctypes.data, array.nbytes))
+
+    def host_unpin(self, array):
+        self._check(load().sangnom_cuda_host_unpin(self._h, array.ctypes.data))
 
     def stats(self):
         s = SnStats()

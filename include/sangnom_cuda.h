@@ -46,7 +46,7 @@ extern "C" {
 #define SN_API
 #endif
 
-#define SANGNOM_CUDA_ABI_VERSION 1
+#define SANGNOM_CUDA_ABI_VERSION 2
 
 typedef struct sn_ctx sn_ctx;
 
@@ -85,14 +85,25 @@ enum sn_mode {
  * (0): opt=0 arithmetic, the parity contract. */
 #define SN_FLAG_SATURATE 2
 
+#define SN_DEVICE_ALL (-1)   /* sn_config.device: one pipeline on every sm_100 device the process can see */
+
 typedef struct sn_config {
     int abi_version;         /* SANGNOM_CUDA_ABI_VERSION */
-    int device;              /* CUDA device ordinal */
+    int device;              /* CUDA device ordinal, or SN_DEVICE_ALL */
     int sample_type;         /* enum sn_sample */
     int pool_width;          /* OUTPUT luma width in samples  (vi.width)            -> S  = align32 */
     int pool_height;         /* OUTPUT luma height in rows    (vi.height after dh)  -> Hb = (h+1)>>1 */
-    int max_frames_in_flight;/* frames resident on the device at once (0 = library default) */
+    int max_frames_in_flight;/* frames resident on ONE device at once (0 = library default) */
     int flags;               /* SN_FLAG_* bits, 0 = defaults */
+    /* Several devices behind one context (host entry). Frames are independent under the parity contract, so the
+     * chunks of consecutive frames a batch is cut into are dealt round-robin to one pipeline per device - own
+     * streams, staging and host thread each, no data exchanged between devices; a frame's planes always stay on one
+     * device (U reads Y's cost state, V reads U's). This is what the reference gets from the host's MT model
+     * (SangNom2.h:63-66, one filter instance per worker thread). Bit d set = use CUDA device d; 0 = `device` alone
+     * (or all devices for SN_DEVICE_ALL). SN_FLAG_PERSISTENT_POOL chains the frames and therefore runs on the first
+     * device only. The device entry always runs on the first device of the context. */
+    unsigned long long device_mask;
+    int copy_threads;        /* host threads (all pipelines together) for the row copies of the host entry; 0 = default */
 } sn_config;
 
 /* One plane of one frame. Pitches are in BYTES. */
@@ -120,8 +131,10 @@ typedef struct sn_limits {
 typedef struct sn_stats {    /* counters since create (or the last reset) */
     uint64_t kernel_launches;
     uint64_t planes_processed;
-    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t h2d_bytes, d2h_bytes;   /* what crossed PCIe: kept rows up, interpolated rows down */
     uint64_t frames;
+    uint64_t host_copy_bytes;        /* rows copied by host threads: kept field + border row source -> destination (the
+                                        reference's BitBlt, :361-391), copied planes, staging of pageable buffers */
 } sn_stats;
 
 /* Create a context on cfg->device. Returns SN_OK and *out, or an error (message via
@@ -129,17 +142,19 @@ typedef struct sn_stats {    /* counters since create (or the last reset) */
 SN_API int sangnom_cuda_create(const sn_config* cfg, sn_ctx** out);
 SN_API void sangnom_cuda_destroy(sn_ctx* ctx);
 
-/* HOST buffers. Pinned (cudaHostAlloc / cudaHostRegister) buffers are DMA'd directly; pageable
- * buffers go through the context's pinned staging. Jobs may be in any order; they are grouped by
- * `frame` and run in plane order. Synchronous: returns when every dst is complete. Frames are
- * pipelined internally (H2D | kernels | D2H on separate streams, four chunks of frames in flight). */
+/* HOST buffers. Pinned (cudaHostAlloc / cudaHostRegister / sangnom_cuda_host_pin) buffers are DMA'd directly;
+ * pageable buffers go through the context's pinned staging. Only the kept field goes up and only the interpolated
+ * rows come down; the kept rows and the border row of dst are copied src -> dst on the host meanwhile (nothing at all
+ * when dst already holds them: src == dst, SN_MODE_FIELD). Jobs may be in any order; they are grouped by `frame`
+ * and run in plane order. Synchronous: returns when every dst is complete. Frames are pipelined internally (host
+ * copies | H2D | kernels | D2H, four chunks of frames in flight per device, one host thread per device). */
 SN_API int sangnom_cuda_process_planes(sn_ctx* ctx, const sn_plane_job* jobs, int njobs);
 
 /* The same work split in two calls so that consecutive batches overlap (batch k+1 uploads while batch k
- * downloads): submit queues the batch and returns a ticket - it blocks only while all chunk slots of the
- * pipeline are occupied; wait returns when every dst of that batch (and of all earlier ones) is complete.
- * The job array is copied; the src/dst BUFFERS must stay valid and untouched until wait returns.
- * process_planes(jobs) == submit(jobs) + wait(ticket). An error in either call drains the whole pipeline. */
+ * downloads): submit validates and queues the batch and returns a ticket without waiting for any device work; wait
+ * returns when every dst of that batch (and of all earlier ones) is complete, or the first error any of them met
+ * (a failed batch does not disturb the others). The job array is copied; the src/dst BUFFERS must stay valid and
+ * untouched until wait returns. process_planes(jobs) == submit(jobs) + wait(ticket). */
 typedef uint64_t sn_ticket;
 SN_API int sangnom_cuda_submit(sn_ctx* ctx, const sn_plane_job* jobs, int njobs, sn_ticket* ticket);
 SN_API int sangnom_cuda_wait(sn_ctx* ctx, sn_ticket ticket);
@@ -165,6 +180,14 @@ SN_API void sangnom_cuda_reset_stats(sn_ctx* ctx);
 /* Pinned host memory helpers for callers that want the zero-staging path. */
 SN_API void* sangnom_cuda_host_alloc(size_t bytes);
 SN_API void sangnom_cuda_host_free(void* p);
+/* Pin a long-lived host range the caller owns (a frame server's recycled frame buffers) so that planes inside it are
+ * DMA'd directly (cudaHostRegister). The range must stay allocated until it is unpinned; everything still pinned is
+ * released by sangnom_cuda_destroy. Pinning costs about a millisecond per few MB: worth it only for buffers that
+ * come back. Returns SN_OK, or SN_ERR_CUDA when the driver refuses (the range then simply stays pageable). */
+SN_API int sangnom_cuda_host_pin(sn_ctx* ctx, void* base, size_t bytes);
+SN_API int sangnom_cuda_host_unpin(sn_ctx* ctx, void* base);
+/* Number of devices (pipelines) behind the context. */
+SN_API int sangnom_cuda_device_count(sn_ctx* ctx);
 
 /* ---- Anti-aliasing chain: SangNom2(dh=true) -> turn -> SangNom2(dh=true) -> turn back, on the device ----------
  * What scripts build from four filters around the reference (README.md:43-46 `dh`; AviSynth TurnRight/TurnLeft or

@@ -52,7 +52,8 @@ int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long lo
         t.thr_i = sample_bytes == 1 ? ((int)thresholds[q] & 0xFF) : ((int)thresholds[q] & 0xFFFF);
         t.in = geo[q].in; t.out = geo[q].out;
         const bool narrow = widths[q] + 8 <= S;
-        const sn::LaunchGeometry g = sn::make_geometry(S, Hb, saturate != 0, narrow);
+        sn::LaunchGeometry g = sn::make_geometry(S, Hb, saturate != 0, narrow);
+        if (sample_bytes == 2) g.key_mask = 0xFFFF0u;                  // like launch_wide()
         const unsigned G = (unsigned)cluster;
         const int cols = sample_bytes == 1 ? sn::u8k::kCols : sn::wide::kCols;
         if (S % (int)(G * cols) != 0) return -1;

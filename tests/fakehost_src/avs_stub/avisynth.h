@@ -121,9 +121,9 @@ struct VideoInfo {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Frames. One heap block per plane; pitch rounded up to the requested alignment.
-// Plane buffers are recycled through a small free list, like AviSynth+'s frame registry: a frame server does not
-// go to the system allocator (and fault in fresh pages) for every output frame.
+// Frames. One heap block (VideoFrameBuffer) per frame holding all planes, like AviSynth+; pitch rounded up to the
+// requested alignment. Frame buffers are recycled through a small free list, like AviSynth+'s frame registry: a frame
+// server does not go to the system allocator (and fault in fresh pages) for every output frame.
 class StubFramePool {
     struct Entry { void* p; size_t bytes, align; };
     static std::mutex& mu() { static std::mutex m; return m; }
@@ -149,11 +149,24 @@ public:
     }
 };
 
+// The block of memory behind a frame (AviSynth+: VideoFrame::GetFrameBuffer()).
+class VideoFrameBuffer {
+    friend class VideoFrame;
+    BYTE* data = nullptr;
+    int data_size = 0;
+public:
+    const BYTE* GetReadPtr() const { return data; }
+    BYTE* GetWritePtr() { return data; }
+    int GetDataSize() const { return data_size; }
+};
+
 class VideoFrame {
     friend class PVideoFrame;
     friend class FakeHostAccess;
     int refcount = 0;
-    struct PlaneBuf { BYTE* data = nullptr; int pitch = 0, row_size = 0, height = 0; size_t bytes = 0, align = 0; };
+    struct PlaneBuf { BYTE* data = nullptr; int pitch = 0, row_size = 0, height = 0; size_t bytes = 0; };
+    VideoFrameBuffer vfb_;
+    size_t vfb_bytes_ = 0, vfb_align_ = 0;
     // buffers go back to the pool of the module that created the frame (this header is compiled into several shared
     // objects, each with its own StubFramePool statics; the destructor may run in any of them)
     void (*release_)(void*, size_t, size_t) = nullptr;
@@ -176,6 +189,7 @@ public:
         static const int ids[4] = { PLANAR_Y, PLANAR_U, PLANAR_V, PLANAR_A };
         if (align < 16) align = 16;
         release_ = &StubFramePool::give;
+        size_t total = 0;
         for (int i = 0; i < n; ++i) {
             PlaneBuf& p = planes_[i];
             const int sw = (i == 1 || i == 2) ? vi.GetPlaneWidthSubsampling(ids[i]) : 0;
@@ -183,16 +197,22 @@ public:
             p.row_size = (vi.width >> sw) * vi.ComponentSize();
             p.height = vi.height >> sh;
             p.pitch = (p.row_size + align - 1) / align * align;
-            const size_t bytes = (size_t)p.pitch * (size_t)std::max(p.height, 1);
-            p.data = static_cast<BYTE*>(StubFramePool::take(bytes, (size_t)align));
-            p.bytes = bytes; p.align = (size_t)align;
-            // New frames hold garbage in a real host; poison them so that reads of never-written
-            // output (e.g. the alpha plane in the reference) are visible in tests. Without poisoning the
-            // memory is left as it is, like a real host's recycled frame buffers.
-            if (poison) std::memset(p.data, 0xCD, bytes);
+            p.bytes = ((size_t)p.pitch * (size_t)std::max(p.height, 1) + (size_t)align - 1) / (size_t)align * (size_t)align;
+            total += p.bytes;
         }
+        vfb_bytes_ = total ? total : 1;
+        vfb_align_ = (size_t)align;
+        vfb_.data = static_cast<BYTE*>(StubFramePool::take(vfb_bytes_, vfb_align_));
+        vfb_.data_size = (int)vfb_bytes_;
+        size_t off = 0;
+        for (int i = 0; i < n; ++i) { planes_[i].data = vfb_.data + off; off += planes_[i].bytes; }
+        // New frames hold garbage in a real host; poison them so that reads of never-written
+        // output (e.g. the alpha plane in the reference) are visible in tests. Without poisoning the
+        // memory is left as it is, like a real host's recycled frame buffers.
+        if (poison) std::memset(vfb_.data, 0xCD, vfb_bytes_);
     }
-    ~VideoFrame() { for (auto& p : planes_) if (p.data) release_(p.data, p.bytes, p.align); }
+    ~VideoFrame() { if (vfb_.data) release_(vfb_.data, vfb_bytes_, vfb_align_); }
+    VideoFrameBuffer* GetFrameBuffer() const { return const_cast<VideoFrameBuffer*>(&vfb_); }
     VideoFrame(const VideoFrame&) = delete;
     VideoFrame& operator=(const VideoFrame&) = delete;
 

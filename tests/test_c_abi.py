@@ -30,7 +30,9 @@ def test_abi_version_and_struct_layout():
     assert lib.sangnom_cuda_abi_version() == int(re.search(r"#define SANGNOM_CUDA_ABI_VERSION (\d+)", HEADER).group(1))
     # sn_plane_job: 2 x (ptr, ptrdiff) + 4 ints + float + 2 ints, 8-byte aligned
     assert C.sizeof(cuda.SnPlaneJob) == 64
-    assert C.sizeof(cuda.SnConfig) == 28
+    # sn_config: 7 ints, pad, u64 device_mask, int copy_threads, pad
+    assert C.sizeof(cuda.SnConfig) == 48 and cuda.SnConfig.device_mask.offset == 32 and cuda.SnConfig.copy_threads.offset == 40
+    assert C.sizeof(cuda.SnStats) == 48
     assert cuda.SnPlaneJob.threshold.offset == 48 and cuda.SnPlaneJob.frame.offset == 56
 
 

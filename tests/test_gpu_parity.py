@@ -146,7 +146,10 @@ def test_separated_fields_input(cuda):
     for i, fr in enumerate(woven):
         exp = O.oracle_frame(fr, fmt.bits, order=0, aa=48, aac=48, parity=parity_of(i))
         assert_planes_equal(got[i][:3], exp[:3], f"fields frame {i}")
-    assert st["h2d_bytes"] * 2 <= st["d2h_bytes"] + 4 * 3 * 16 * 288      # staged rows are padded to 16 bytes
+    frame_bytes = sum(p.nbytes for p in woven[0][:3])
+    pad = 4 * 3 * 32 * 288                                                  # staged rows are padded to 16 / 32 bytes
+    assert st["h2d_bytes"] <= 4 * frame_bytes // 2 + pad                    # the kept field goes up ...
+    assert st["d2h_bytes"] <= 4 * frame_bytes // 2 + pad                    # ... and only the interpolated rows come down
 
 
 SATURATING = [("yv12_720", "YV12", 720, 480, dict(order=1, aa=48, aac=48)), ("420p8_1080p", "YUV420P8", 1920, 1080, dict(order=0, aa=48, aac=48)),
@@ -175,3 +178,86 @@ def test_saturating_flavour(cuda, case):
         wrap = O.oracle_frame(fr, fmt.bits, parity=parity_of(i), **args)
         differs |= any(not np.array_equal(a, b) for a, b in zip(exp[:3], wrap[:3]))
     assert differs or fmt.sample_bytes == 4 or fmt.bits == 10
+
+
+@pytest.mark.parametrize("pinned", [True, False], ids=["pinned", "pageable"])
+@pytest.mark.parametrize("fmtname", ["YUV420P8", "YUV422P10", "YUV444PS"])
+def test_host_path_moves_half_a_frame_each_way(cuda, pinned, fmtname):
+    """Full frames in (SN_MODE_FIELD), full frames out, but PCIe carries only the kept rows up and the interpolated
+    rows down; kept rows and border row of dst are filled on the host (reference GetFrame :361-391). Also: src == dst
+    (the kept field already sits in the destination frame) needs no host copy of kept rows at all."""
+    from oracle import oracle as O
+    from pysangnom.clips import make_frame
+    from pysangnom.formats import FORMATS
+    fmt, w, h, nf = FORMATS[fmtname], 352, 288, 5
+    frames = [make_frame(61, w, h, fmt, "noise", i) for i in range(nf)]
+    alloc = (lambda a: cuda.pinned_empty(a.shape, a.dtype)) if pinned else (lambda a: np.empty_like(a))
+    with cuda.Context(fmt.sample_bytes, w, h, max_frames_in_flight=8) as ctx:
+        jobs, outs, keep = [], [], []
+        for k, planes in enumerate(frames):
+            srcs = [alloc(p) for p in planes[:3]]
+            dsts = [alloc(p) for p in planes[:3]]
+            for s_, d, p in zip(srcs, dsts, planes):
+                s_[...] = p
+                d[...] = 0x55 if fmt.sample_bytes < 4 else 0.25
+            keep.append(srcs)
+            jobs += ctx.frame_jobs(srcs, dsts, fmt.bits, order=0, aa=48, aac=48, parity=parity_of(k), frame_key=k)
+            outs.append(dsts)
+        ctx.process_jobs(jobs)
+        st = ctx.stats()
+        frame_bytes = sum(p.nbytes for p in frames[0][:3])
+        pad = nf * 3 * 32 * h
+        assert st["h2d_bytes"] <= nf * frame_bytes // 2 + pad and st["d2h_bytes"] <= nf * frame_bytes // 2 + pad
+        assert st["h2d_bytes"] >= nf * frame_bytes // 2 - pad
+        for k, planes in enumerate(frames):
+            exp = O.oracle_frame(planes, fmt.bits, order=0, aa=48, aac=48, parity=parity_of(k))
+            assert_planes_equal(outs[k], exp[:3], f"{fmtname} frame {k}")
+        # in place on the host: the destination frame already holds the kept field (and garbage in the other rows)
+        ctx.reset_stats()
+        inplace = [[alloc(p) for p in planes[:3]] for planes in frames]
+        jobs = []
+        for k, planes in enumerate(frames):
+            off = cuda.resolve_offset(0, parity_of(k))
+            for b, p in zip(inplace[k], planes):
+                b[...] = 0x33 if fmt.sample_bytes < 4 else 0.75
+                b[off::2] = p[off::2]
+            jobs += ctx.frame_jobs(inplace[k], inplace[k], fmt.bits, order=0, aa=48, aac=48, parity=parity_of(k), frame_key=k)
+        ctx.process_jobs(jobs)
+        st2 = ctx.stats()
+        for k, planes in enumerate(frames):
+            exp = O.oracle_frame(planes, fmt.bits, order=0, aa=48, aac=48, parity=parity_of(k))
+            assert_planes_equal(inplace[k], exp[:3], f"{fmtname} in place frame {k}")
+        assert st2["host_copy_bytes"] < st["host_copy_bytes"]
+
+
+def test_failed_batch_does_not_disturb_its_neighbours(cuda):
+    """A batch that fails validation is refused at submit; batches submitted before and after it complete, and their
+    wait() reports success (each batch carries its own status)."""
+    from oracle import oracle as O
+    from pysangnom.clips import make_frame
+    from pysangnom.formats import FORMATS
+    fmt, w, h = FORMATS["YUV420P8"], 176, 144
+    frames = [make_frame(5, w, h, fmt, "edges", i) for i in range(6)]
+    with cuda.Context(fmt.sample_bytes, w, h, max_frames_in_flight=4) as ctx:
+        def batch(lo, hi):
+            jobs, outs, keep = [], [], []
+            for k in range(lo, hi):
+                srcs = [np.ascontiguousarray(p) for p in frames[k][:3]]
+                dsts = [np.zeros_like(p) for p in srcs]
+                keep.append(srcs)
+                jobs += ctx.frame_jobs(srcs, dsts, fmt.bits, order=0, aa=48, aac=48, parity=parity_of(k), frame_key=k)
+                outs.append(dsts)
+            return jobs, outs, keep
+        j1, o1, k1 = batch(0, 3)
+        t1 = ctx.submit(j1)
+        bad = list(batch(3, 4)[0])
+        bad[0].dst_height = 143                                           # odd height: refused
+        with pytest.raises(cuda.SangNomCudaError):
+            ctx.submit(bad)
+        j2, o2, k2 = batch(3, 6)
+        t2 = ctx.submit(j2)
+        ctx.wait(t2)
+        ctx.wait(t1)
+    for k in range(6):
+        exp = O.oracle_frame(frames[k], fmt.bits, order=0, aa=48, aac=48, parity=parity_of(k))
+        assert_planes_equal((o1 + o2)[k], exp[:3], f"frame {k}")
