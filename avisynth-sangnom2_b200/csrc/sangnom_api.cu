@@ -497,11 +497,8 @@ static int submit_impl(sn_ctx* ctx, const sn_plane_job* user_jobs, int njobs, sn
     *ticket = batch->ticket;
     Batch* const b = batch.get();
     ctx->batches.push_back(std::move(batch));
-    for (size_t k = 0; k < nchunks; ++k) {
-        Pipeline& pl = *ctx->pipelines[ctx->next_pipeline];
-        ctx->next_pipeline = (ctx->next_pipeline + 1) % ctx->pipelines.size();
-        pl.push(Chunk{ b, k * chunk_frames, std::min(nframes, (k + 1) * chunk_frames) });
-    }
+    sn::plan_chunks(nframes, chunk_frames, (int)ctx->pipelines.size(), ctx->next_pipeline,
+                    [&](const sn::ChunkDeal& d) { ctx->pipelines[(size_t)d.pipeline]->push(Chunk{ b, d.first, d.last }); });
     return SN_OK;
 }
 

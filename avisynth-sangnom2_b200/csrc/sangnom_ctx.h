@@ -111,7 +111,7 @@ constexpr int kSlots = 4;
 struct Slot {
     DevBuf planes, state, tasks;
     PinnedBuf tasks_host, stage_in, stage_out;
-    cudaStream_t compute = nullptr;
+    cudaStream_t compute = nullptr, h2d = nullptr, d2h = nullptr;
     cudaEvent_t h2d_done = nullptr, kernels_done = nullptr, d2h_done = nullptr;
     cudaEvent_t t_h2d0 = nullptr, t_k0 = nullptr, t_d2h0 = nullptr;          // SANGNOM_TRACE only
     bool busy = false;

@@ -121,7 +121,7 @@ cudaError_t launch_wide_variant(const PlaneTask* tasks, int ntasks, LaunchGeomet
 template <typename T>
 cudaError_t launch_wide(const PlaneTask* tasks, int ntasks, LaunchGeometry g, cudaStream_t stream)
 {
-    const int seg_max = std::min(std::max(env_int("SANGNOM_WIDE_SEG", 1024), 128), 1024);   // tuning / test knob, read per launch
+    const int seg_max = std::min(std::max(env_int("SANGNOM_WIDE_SEG", 512), 128), 1024);   // tuning / test knob, read per launch
     const int G = cluster_split(g.S, seg_max, 1024, wide::kCols);
     if (G == 0) return cudaErrorInvalidValue;
     const int seg = g.S / G;

@@ -92,6 +92,10 @@ cudaError_t flush_segments(std::vector<Segment>& v, cudaMemcpyKind kind, cudaStr
 }
 
 const bool g_trace = getenv("SANGNOM_TRACE") != nullptr;
+// SANGNOM_B200_COPY_STREAMS=shared: all chunks of a pipeline upload on one stream and download on another (one DMA
+// engine per direction). Default: every slot has its own pair, so that the 2-D transfers of consecutive chunks can
+// run on different copy engines at the same time.
+const bool g_shared_copy_streams = [] { const char* v = getenv("SANGNOM_B200_COPY_STREAMS"); return v && std::strcmp(v, "shared") == 0; }();
 
 // The kept rows of a job in host memory: first row and the step between consecutive kept rows (bytes).
 inline const char* kept_rows(const sn_plane_job& jb, ptrdiff_t& step)
@@ -114,6 +118,8 @@ Pipeline::~Pipeline()
         s.planes.release(); s.state.release(); s.tasks.release();
         s.tasks_host.release(); s.stage_in.release(); s.stage_out.release();
         if (s.compute) cudaStreamDestroy(s.compute);
+        if (s.h2d && s.h2d != h2d_) cudaStreamDestroy(s.h2d);
+        if (s.d2h && s.d2h != d2h_) cudaStreamDestroy(s.d2h);
         for (cudaEvent_t e : { s.h2d_done, s.kernels_done, s.d2h_done, s.t_h2d0, s.t_k0, s.t_d2h0 })
             if (e) cudaEventDestroy(e);
     }
@@ -131,6 +137,11 @@ cudaError_t Pipeline::init()
     if ((e = cudaStreamCreateWithFlags(&d2h_, cudaStreamNonBlocking)) != cudaSuccess) return e;
     for (Slot& s : slots_) {
         if ((e = cudaStreamCreateWithFlags(&s.compute, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if (g_shared_copy_streams || ctx_->persistent) { s.h2d = h2d_; s.d2h = d2h_; }
+        else {
+            if ((e = cudaStreamCreateWithFlags(&s.h2d, cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaStreamCreateWithFlags(&s.d2h, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        }
         for (cudaEvent_t* ev : { &s.h2d_done, &s.kernels_done, &s.d2h_done })
             if ((e = cudaEventCreateWithFlags(ev, g_trace ? cudaEventDefault : cudaEventDisableTiming)) != cudaSuccess) return e;
         if (g_trace)
@@ -305,7 +316,7 @@ int Pipeline::start_chunk(Slot& s, const Chunk& c, std::string& err)
 
         // ---- upload of the kept rows ----
         uint64_t h2d_bytes = 0, d2h_bytes = 0;
-        if (g_trace) cudaEventRecord(s.t_h2d0, h2d_);
+        if (g_trace) cudaEventRecord(s.t_h2d0, s.h2d);
         std::vector<std::vector<sn::PlaneTask>> by_pass;
         std::vector<Segment> up_segs, down_segs;
         for (size_t k = c.first; k < c.last && status == SN_OK; ++k) {
@@ -321,8 +332,8 @@ int Pipeline::start_chunk(Slot& s, const Chunk& c, std::string& err)
                 if (p.up == Pass::STAGED) add_segment(up_segs, static_cast<char*>(s.stage_in.p) + p.stage_in_off, dsrc, p.src_pitch * p.n, -1);
                 else if (p.up == Pass::LINEAR) add_segment(up_segs, const_cast<char*>(kept), dsrc, row * p.n, p.src_pinned);
                 else {
-                    PL_CUDA(flush_segments(up_segs, cudaMemcpyHostToDevice, h2d_), "H2D copy");           // keep submission order
-                    PL_CUDA(cudaMemcpy2DAsync(dsrc, p.src_pitch, kept, (size_t)step, row, (size_t)p.n, cudaMemcpyHostToDevice, h2d_), "H2D copy");
+                    PL_CUDA(flush_segments(up_segs, cudaMemcpyHostToDevice, s.h2d), "H2D copy");           // keep submission order
+                    PL_CUDA(cudaMemcpy2DAsync(dsrc, p.src_pitch, kept, (size_t)step, row, (size_t)p.n, cudaMemcpyHostToDevice, s.h2d), "H2D copy");
                 }
                 h2d_bytes += p.up == Pass::PITCHED ? row * p.n : p.src_pitch * p.n;
                 // Picture row offset+1+2j of the plane is packed row j of the block at out_off: hand the kernel a pitch of
@@ -333,23 +344,23 @@ int Pipeline::start_chunk(Slot& s, const Chunk& c, std::string& err)
             }
         }
         if (status != SN_OK) break;
-        PL_CUDA(flush_segments(up_segs, cudaMemcpyHostToDevice, h2d_), "H2D copy");
+        PL_CUDA(flush_segments(up_segs, cudaMemcpyHostToDevice, s.h2d), "H2D copy");
         // The task array rides the upload stream too: a small copy on the compute stream would queue on the
         // same DMA engine behind the NEXT chunks' bulk uploads and hold this chunk's kernels back.
-        PL_CUDA(upload_tasks(by_pass, static_cast<sn::PlaneTask*>(s.tasks_host.p), static_cast<sn::PlaneTask*>(s.tasks.p), h2d_), "task upload");
+        PL_CUDA(upload_tasks(by_pass, static_cast<sn::PlaneTask*>(s.tasks_host.p), static_cast<sn::PlaneTask*>(s.tasks.p), s.h2d), "task upload");
         // persistent pool: every chunk's kernels on ONE stream, so that frames run in submission order across chunks
         const cudaStream_t compute = ctx->persistent ? slots_[0].compute : s.compute;
-        PL_CUDA(cudaEventRecord(s.h2d_done, h2d_), "event");
+        PL_CUDA(cudaEventRecord(s.h2d_done, s.h2d), "event");
         PL_CUDA(cudaStreamWaitEvent(compute, s.h2d_done, 0), "event");
 
         // ---- kernels ----
         if (g_trace) cudaEventRecord(s.t_k0, compute);
         PL_CUDA(launch_passes(ctx, by_pass, static_cast<sn::PlaneTask*>(s.tasks.p), compute), "kernel launch");
         PL_CUDA(cudaEventRecord(s.kernels_done, compute), "event");
-        PL_CUDA(cudaStreamWaitEvent(d2h_, s.kernels_done, 0), "event");
+        PL_CUDA(cudaStreamWaitEvent(s.d2h, s.kernels_done, 0), "event");
 
         // ---- download of the interpolated rows ----
-        if (g_trace) cudaEventRecord(s.t_d2h0, d2h_);
+        if (g_trace) cudaEventRecord(s.t_d2h0, s.d2h);
         for (size_t k = c.first; k < c.last && status == SN_OK; ++k) {
             for (Pass& p : frames[k].passes) {
                 if (p.n < 2) continue;
@@ -360,16 +371,16 @@ int Pipeline::start_chunk(Slot& s, const Chunk& c, std::string& err)
                     add_segment(down_segs, static_cast<char*>(s.stage_out.p) + p.stage_out_off, dout, p.out_pitch * (size_t)(p.n - 1), -1);
                     d2h_bytes += p.out_pitch * (size_t)(p.n - 1);
                 } else {
-                    PL_CUDA(flush_segments(down_segs, cudaMemcpyDeviceToHost, d2h_), "D2H copy");
+                    PL_CUDA(flush_segments(down_segs, cudaMemcpyDeviceToHost, s.d2h), "D2H copy");
                     PL_CUDA(cudaMemcpy2DAsync(static_cast<char*>(jb.dst) + (ptrdiff_t)(jb.offset + 1) * jb.dst_pitch, 2 * (size_t)jb.dst_pitch, dout, p.out_pitch,
-                                              row, (size_t)(p.n - 1), cudaMemcpyDeviceToHost, d2h_), "D2H copy");
+                                              row, (size_t)(p.n - 1), cudaMemcpyDeviceToHost, s.d2h), "D2H copy");
                     d2h_bytes += row * (size_t)(p.n - 1);
                 }
             }
         }
         if (status != SN_OK) break;
-        PL_CUDA(flush_segments(down_segs, cudaMemcpyDeviceToHost, d2h_), "D2H copy");
-        PL_CUDA(cudaEventRecord(s.d2h_done, d2h_), "event");
+        PL_CUDA(flush_segments(down_segs, cudaMemcpyDeviceToHost, s.d2h), "D2H copy");
+        PL_CUDA(cudaEventRecord(s.d2h_done, s.d2h), "event");
         s.busy = true;
         s.chunk = c;
         {
@@ -382,9 +393,9 @@ int Pipeline::start_chunk(Slot& s, const Chunk& c, std::string& err)
 
     if (status != SN_OK) {
         // leave nothing of this chunk in flight that reads or writes user memory
-        cudaStreamSynchronize(h2d_);
+        cudaStreamSynchronize(s.h2d);
         cudaStreamSynchronize(ctx->persistent ? slots_[0].compute : s.compute);
-        cudaStreamSynchronize(d2h_);
+        cudaStreamSynchronize(s.d2h);
         cudaGetLastError();
     }
     return status;

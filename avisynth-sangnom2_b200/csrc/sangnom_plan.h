@@ -97,6 +97,20 @@ inline void plan_attach_carry(CostState& first_in, CostState& last_out, void* ca
     last_out = CostState{ nullptr, carry_out, 0, 0, 1, Hb - 1 };
 }
 
+// Several devices behind one context: a batch of frames is cut into chunks of consecutive frames and the chunks are
+// dealt round-robin to the devices' pipelines, continuing where the previous batch stopped (`next`). A frame is never
+// split - its planes share cost state - and no data moves between devices.
+struct ChunkDeal { size_t first, last; int pipeline; };        // frames [first, last) of the batch
+template <typename Emit>
+inline void plan_chunks(size_t nframes, size_t chunk_frames, int npipelines, size_t& next, Emit&& emit)
+{
+    if (chunk_frames == 0) chunk_frames = 1;
+    for (size_t first = 0; first < nframes; first += chunk_frames) {
+        emit(ChunkDeal{ first, std::min(nframes, first + chunk_frames), (int)next });
+        next = (next + 1) % (size_t)std::max(npipelines, 1);
+    }
+}
+
 inline void plan_place_state(CostState& s, char* base)
 {
     if (s.a) s.a = base + (reinterpret_cast<size_t>(s.a) - 1);

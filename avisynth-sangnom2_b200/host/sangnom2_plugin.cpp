@@ -69,9 +69,9 @@ SangNom2::SangNom2(PClip _child, int order, int aa, int aac, int threads, bool d
     cfg.pool_width = vi.width;       // pool geometry comes from the OUTPUT luma size (:287-288)
     cfg.pool_height = vi.height;
     // frames fetched and processed per cache miss on sequential access: enough to keep the device pipeline busy, but
-    // bounded by the memory the finished frames occupy until they are served (about 128 MB per batch by default)
+    // bounded by the memory the finished frames occupy until they are served (about 512 MB per batch by default)
     const long long frame_bytes = (long long)vi.width * vi.height * sample_bytes_ * (plane_count_ == 1 ? 2 : 3) / 2 + 1;
-    const int default_batch = (int)std::max(4LL, std::min(32LL, (128LL << 20) / frame_bytes));
+    const int default_batch = (int)std::max(4LL, std::min(128LL, (512LL << 20) / frame_bytes));
     batch_frames_ = env_int("SANGNOM_B200_BATCH", default_batch, 1, 256);
     cfg.max_frames_in_flight = batch_frames_ < 3 ? 3 : batch_frames_;
     // SANGNOM_B200_PERSISTENT=1: keep the scratch-pool state from frame to frame like one long-lived reference

@@ -134,6 +134,19 @@ int emul_copy_pool_selftest(int threads, int rounds, unsigned seed)
     return 0;
 }
 
+// The host entry's chunk dealing (sangnom_plan.h plan_chunks): writes (first, last, pipeline) triples, returns the count.
+int emul_deal_chunks(long long nframes, long long chunk_frames, int npipelines, long long* next, long long* out, int max_out)
+{
+    size_t nx = (size_t)*next;
+    int n = 0;
+    sn::plan_chunks((size_t)nframes, (size_t)chunk_frames, npipelines, nx, [&](const sn::ChunkDeal& d) {
+        if (n < max_out) { out[3 * n] = (long long)d.first; out[3 * n + 1] = (long long)d.last; out[3 * n + 2] = d.pipeline; }
+        ++n;
+    });
+    *next = (long long)nx;
+    return n;
+}
+
 size_t emul_carry_bytes(int sample_bytes, int pool_width, int pool_height)
 {
     return sn::plan_carry_bytes((pool_width + 31) & ~31, (pool_height + 1) >> 1, sample_bytes);

@@ -83,3 +83,31 @@ def test_two_ranks_cover_the_clip_once():
         out = O.oracle_frame(make_frame(9, 64, 32, FORMATS["YV12"], "noise", n), 8, order=0, aa=48, aac=48, parity=(n % 2 == 0))
         h = hashlib.sha256(b"".join(p.tobytes() for p in out)).digest()
         assert sums[n] == int.from_bytes(h[:7], "little")
+
+
+@pytest.mark.parametrize("nframes,chunk,ndev", [(0, 4, 2), (1, 4, 2), (37, 9, 2), (592, 37, 8), (100, 7, 3), (5, 100, 4)])
+def test_chunks_of_a_batch_are_dealt_round_robin_over_the_devices(nframes, chunk, ndev):
+    """The multi-device context (one pipeline per GPU behind one sn_ctx): every frame of every batch lands in exactly
+    one chunk, chunks are runs of consecutive frames, and consecutive chunks - across batches too - go to consecutive
+    devices. The dealing is the pure function the library's submit uses (csrc/sangnom_plan.h plan_chunks)."""
+    import ctypes as C
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    subprocess.run(["make", "-f", os.path.join(here, "emul", "Makefile")], check=True, stdout=subprocess.DEVNULL)
+    L = C.CDLL(os.path.join(here, "emul", "libkernel_emul.so"))
+    L.emul_deal_chunks.restype = C.c_int
+    L.emul_deal_chunks.argtypes = [C.c_longlong, C.c_longlong, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]
+    nxt = C.c_longlong(0)
+    seen_devices = []
+    for batch in range(3):
+        out = (C.c_longlong * (3 * 1024))()
+        n = L.emul_deal_chunks(nframes, chunk, ndev, C.byref(nxt), out, 1024)
+        deals = [(out[3 * i], out[3 * i + 1], out[3 * i + 2]) for i in range(n)]
+        assert n == (nframes + chunk - 1) // chunk
+        covered = []
+        for first, last, dev in deals:
+            assert 0 <= dev < ndev and first < last <= nframes and last - first <= chunk
+            covered += list(range(first, last))
+            seen_devices.append(dev)
+        assert covered == list(range(nframes))
+    assert seen_devices == [i % ndev for i in range(len(seen_devices))]
