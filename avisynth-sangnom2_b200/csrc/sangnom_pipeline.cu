@@ -97,6 +97,39 @@ const bool g_trace = getenv("SANGNOM_TRACE") != nullptr;
 // run on different copy engines at the same time.
 const bool g_shared_copy_streams = [] { const char* v = getenv("SANGNOM_B200_COPY_STREAMS"); return v && std::strcmp(v, "shared") == 0; }();
 
+// Planes of consecutive frames that a batching host layer staged back to back in one pinned arena sit at a constant
+// stride: the same rows of all of them are ONE 3-D transfer (width = row bytes, height = rows, depth = frames) instead
+// of one 2-D transfer per plane. On the copy engines of this box that is the difference between 26 and 41 GB/s per
+// direction with both directions busy (tools/dma_probe.cu): a 2-D copy of a few hundred rows is dominated by its
+// set-up. A run is formed per (pass index, geometry, field offset): with alternating field parity the even and the
+// odd frames of a clip form two interleaved runs.
+struct Run {
+    std::vector<Pass*> passes;
+    const char* first = nullptr;     // host address of the first row of the first plane
+    ptrdiff_t stride = 0;            // host bytes from one plane of the run to the next (0: single plane so far)
+    size_t row = 0, step = 0;        // row bytes, host bytes between consecutive rows
+    int rows = 0, q = 0, offset = 0, alloc = 0;
+};
+
+// Append plane `p` (rows start at `host`) to the open run with the same key, or open a new one.
+void add_to_runs(std::vector<Run>& runs, Pass* p, int q, const char* host, size_t row, size_t step, int rows, int alloc)
+{
+    for (auto it = runs.rbegin(); it != runs.rend(); ++it) {
+        Run& r = *it;
+        if (r.q != q || r.offset != p->job->offset || r.row != row || r.step != step || r.rows != rows || r.alloc != alloc) continue;
+        const char* last = r.first + (ptrdiff_t)(r.passes.size() - 1) * r.stride;
+        const ptrdiff_t d = host - last;
+        if (r.passes.size() == 1) {
+            // the slice pitch of a 3-D copy is a whole number of rows and must hold the rows copied
+            if (d > 0 && (size_t)d % step == 0 && (size_t)d / step >= (size_t)rows) { r.stride = d; r.passes.push_back(p); return; }
+        } else if (d == r.stride) { r.passes.push_back(p); return; }
+        break;                                   // the newest run with this key does not continue: start another
+    }
+    Run r;
+    r.passes.push_back(p); r.first = host; r.row = row; r.step = step; r.rows = rows; r.q = q; r.offset = p->job->offset; r.alloc = alloc;
+    runs.push_back(r);
+}
+
 // The kept rows of a job in host memory: first row and the step between consecutive kept rows (bytes).
 inline const char* kept_rows(const sn_plane_job& jb, ptrdiff_t& step)
 {
@@ -241,25 +274,41 @@ int Pipeline::start_chunk(Slot& s, const Chunk& c, std::string& err)
     // each filled in job order at 16 / 32-byte granules, so that planes which are neighbours inside one pinned host
     // allocation (or in the slot's own staging) are neighbours on the device and their DMA transfers merge into one
     size_t src_total = 0, out_total = 0, state_bytes = 0, in_bytes = 0, out_bytes = 0, ntasks = 0;
+    std::vector<Run> up_runs, down_runs;             // pinned planes that travel by 2-D / 3-D DMA
     for (size_t k = c.first; k < c.last; ++k) {
         FramePlan& f = frames[k];
         f.state_off = state_bytes;
         state_bytes += align_up(f.state_bytes, 256);
-        for (Pass& p : f.passes) {
+        for (size_t q = 0; q < f.passes.size(); ++q) {
+            Pass& p = f.passes[q];
             const sn_plane_job& jb = *p.job;
             const size_t row = (size_t)p.W * sb;
-            if (!p.src_pinned) { p.up = Pass::STAGED; p.src_pitch = align_up(row, 16); p.stage_in_off = in_bytes; in_bytes += p.src_pitch * p.n; }
-            else if (jb.mode != SN_MODE_FIELD && (size_t)jb.src_pitch == row && row % 16 == 0) { p.up = Pass::LINEAR; p.src_pitch = row; }
-            else { p.up = Pass::PITCHED; p.src_pitch = align_up(row, 16); }
-            p.src_off = src_total; src_total += p.src_pitch * p.n;
             // 32-byte rows: half a row (the pitch the kernel is given, see below) stays a multiple of its widest store
             p.out_pitch = align_up(row, 32);
-            p.out_off = out_total; out_total += p.out_pitch * (size_t)(p.n - 1);
+            if (!p.src_pinned) { p.up = Pass::STAGED; p.src_pitch = align_up(row, 16); p.stage_in_off = in_bytes; in_bytes += p.src_pitch * p.n; }
+            else if (jb.mode != SN_MODE_FIELD && (size_t)jb.src_pitch == row && row % 16 == 0) { p.up = Pass::LINEAR; p.src_pitch = row; }
+            else {
+                p.up = Pass::PITCHED; p.src_pitch = align_up(row, 16);
+                ptrdiff_t step;
+                const char* kept = kept_rows(jb, step);
+                add_to_runs(up_runs, &p, (int)q, kept, row, (size_t)step, p.n, p.src_pinned);
+            }
             if (!p.dst_pinned) { p.down = Pass::STAGED; p.stage_out_off = out_bytes; out_bytes += p.out_pitch * (size_t)(p.n - 1); }
-            else p.down = Pass::PITCHED;
+            else {
+                p.down = Pass::PITCHED;
+                if (p.n > 1) add_to_runs(down_runs, &p, (int)q, static_cast<const char*>(jb.dst) + (ptrdiff_t)(jb.offset + 1) * jb.dst_pitch, row, 2 * (size_t)jb.dst_pitch, p.n - 1, p.dst_pinned);
+            }
+            // staged and linear planes keep job order (that is what lets their transfers merge); run members are placed below
+            if (p.up != Pass::PITCHED) { p.src_off = src_total; src_total += p.src_pitch * p.n; }
+            if (p.down != Pass::PITCHED || p.n < 2) { p.out_off = out_total; out_total += p.out_pitch * (size_t)(p.n - 1); }
             ++ntasks;
         }
     }
+    // the planes of a run back to back on the device: the device side of the 3-D transfer has a slice of exactly `rows` rows
+    for (Run& r : up_runs)
+        for (Pass* p : r.passes) { p->src_off = src_total; src_total += p->src_pitch * p->n; }
+    for (Run& r : down_runs)
+        for (Pass* p : r.passes) { p->out_off = out_total; out_total += p->out_pitch * (size_t)(p->n - 1); }
     // the kernel's border-row store is switched off (no_border), but rows are addressed relative to a pointer two
     // packed half-rows before the block: keep a margin in front of it inside the allocation
     const size_t out_base = align_up(src_total, 256) + 256;
@@ -331,11 +380,7 @@ int Pipeline::start_chunk(Slot& s, const Chunk& c, std::string& err)
                 char* const dsrc = dplanes + p.src_off;
                 if (p.up == Pass::STAGED) add_segment(up_segs, static_cast<char*>(s.stage_in.p) + p.stage_in_off, dsrc, p.src_pitch * p.n, -1);
                 else if (p.up == Pass::LINEAR) add_segment(up_segs, const_cast<char*>(kept), dsrc, row * p.n, p.src_pinned);
-                else {
-                    PL_CUDA(flush_segments(up_segs, cudaMemcpyHostToDevice, s.h2d), "H2D copy");           // keep submission order
-                    PL_CUDA(cudaMemcpy2DAsync(dsrc, p.src_pitch, kept, (size_t)step, row, (size_t)p.n, cudaMemcpyHostToDevice, s.h2d), "H2D copy");
-                }
-                h2d_bytes += p.up == Pass::PITCHED ? row * p.n : p.src_pitch * p.n;
+                h2d_bytes += p.up == Pass::PITCHED ? row * p.n : p.src_pitch * p.n;           // (pitched planes travel with their run, below)
                 // Picture row offset+1+2j of the plane is packed row j of the block at out_off: hand the kernel a pitch of
                 // half a packed row and a plane pointer (offset+1) half-rows before the block.
                 char* const dout = dplanes + out_base + p.out_off;
@@ -345,6 +390,21 @@ int Pipeline::start_chunk(Slot& s, const Chunk& c, std::string& err)
         }
         if (status != SN_OK) break;
         PL_CUDA(flush_segments(up_segs, cudaMemcpyHostToDevice, s.h2d), "H2D copy");
+        for (const Run& r : up_runs) {
+            const Pass& p0 = *r.passes.front();
+            char* const dev = dplanes + p0.src_off;
+            if (r.passes.size() == 1) {
+                PL_CUDA(cudaMemcpy2DAsync(dev, p0.src_pitch, r.first, r.step, r.row, (size_t)r.rows, cudaMemcpyHostToDevice, s.h2d), "H2D copy");
+            } else {
+                cudaMemcpy3DParms q3{};
+                q3.srcPtr = make_cudaPitchedPtr(const_cast<char*>(r.first), r.step, r.row, (size_t)r.stride / r.step);
+                q3.dstPtr = make_cudaPitchedPtr(dev, p0.src_pitch, r.row, (size_t)r.rows);
+                q3.extent = make_cudaExtent(r.row, (size_t)r.rows, r.passes.size());
+                q3.kind = cudaMemcpyHostToDevice;
+                PL_CUDA(cudaMemcpy3DAsync(&q3, s.h2d), "H2D copy");
+            }
+        }
+        if (status != SN_OK) break;
         // The task array rides the upload stream too: a small copy on the compute stream would queue on the
         // same DMA engine behind the NEXT chunks' bulk uploads and hold this chunk's kernels back.
         PL_CUDA(upload_tasks(by_pass, static_cast<sn::PlaneTask*>(s.tasks_host.p), static_cast<sn::PlaneTask*>(s.tasks.p), s.h2d), "task upload");
@@ -361,25 +421,30 @@ int Pipeline::start_chunk(Slot& s, const Chunk& c, std::string& err)
 
         // ---- download of the interpolated rows ----
         if (g_trace) cudaEventRecord(s.t_d2h0, s.d2h);
-        for (size_t k = c.first; k < c.last && status == SN_OK; ++k) {
+        for (size_t k = c.first; k < c.last; ++k)
             for (Pass& p : frames[k].passes) {
                 if (p.n < 2) continue;
-                const sn_plane_job& jb = *p.job;
-                const size_t row = (size_t)p.W * sb;
-                char* const dout = dplanes + out_base + p.out_off;
                 if (p.down == Pass::STAGED) {
-                    add_segment(down_segs, static_cast<char*>(s.stage_out.p) + p.stage_out_off, dout, p.out_pitch * (size_t)(p.n - 1), -1);
+                    add_segment(down_segs, static_cast<char*>(s.stage_out.p) + p.stage_out_off, dplanes + out_base + p.out_off, p.out_pitch * (size_t)(p.n - 1), -1);
                     d2h_bytes += p.out_pitch * (size_t)(p.n - 1);
-                } else {
-                    PL_CUDA(flush_segments(down_segs, cudaMemcpyDeviceToHost, s.d2h), "D2H copy");
-                    PL_CUDA(cudaMemcpy2DAsync(static_cast<char*>(jb.dst) + (ptrdiff_t)(jb.offset + 1) * jb.dst_pitch, 2 * (size_t)jb.dst_pitch, dout, p.out_pitch,
-                                              row, (size_t)(p.n - 1), cudaMemcpyDeviceToHost, s.d2h), "D2H copy");
-                    d2h_bytes += row * (size_t)(p.n - 1);
-                }
+                } else d2h_bytes += (size_t)p.W * sb * (size_t)(p.n - 1);
+            }
+        PL_CUDA(flush_segments(down_segs, cudaMemcpyDeviceToHost, s.d2h), "D2H copy");
+        for (const Run& r : down_runs) {
+            const Pass& p0 = *r.passes.front();
+            char* const dev = dplanes + out_base + p0.out_off;
+            if (r.passes.size() == 1) {
+                PL_CUDA(cudaMemcpy2DAsync(const_cast<char*>(r.first), r.step, dev, p0.out_pitch, r.row, (size_t)r.rows, cudaMemcpyDeviceToHost, s.d2h), "D2H copy");
+            } else {
+                cudaMemcpy3DParms q3{};
+                q3.srcPtr = make_cudaPitchedPtr(dev, p0.out_pitch, r.row, (size_t)r.rows);
+                q3.dstPtr = make_cudaPitchedPtr(const_cast<char*>(r.first), r.step, r.row, (size_t)r.stride / r.step);
+                q3.extent = make_cudaExtent(r.row, (size_t)r.rows, r.passes.size());
+                q3.kind = cudaMemcpyDeviceToHost;
+                PL_CUDA(cudaMemcpy3DAsync(&q3, s.d2h), "D2H copy");
             }
         }
         if (status != SN_OK) break;
-        PL_CUDA(flush_segments(down_segs, cudaMemcpyDeviceToHost, s.d2h), "D2H copy");
         PL_CUDA(cudaEventRecord(s.d2h_done, s.d2h), "event");
         s.busy = true;
         s.chunk = c;

@@ -48,7 +48,7 @@ class SangNom2 : public GenericVideoFilter {
     // while no batch is in flight. SANGNOM_B200_PIN_MB=0 switches it off (see INTEGRATION.md for when to do that).
     struct PinEntry { size_t bytes = 0; int seen = 0; uint64_t last_use = 0; bool pinned = false; };
     std::unordered_map<const void*, PinEntry> pins_;
-    size_t pinned_bytes_ = 0, pin_budget_ = 0;
+    size_t pinned_bytes_ = 0, pin_budget_ = 0, pin_min_bytes_ = 0;
     uint64_t pin_clock_ = 0;
     void note_frame_buffer(const PVideoFrame& f);
 

@@ -81,6 +81,11 @@ SangNom2::SangNom2(PClip _child, int order, int aa, int aac, int threads, bool d
     if (opt == 1 || (opt < 0 && (env->GetCPUFlags() & CPUF_SSE2))) cfg.flags |= SN_FLAG_SATURATE;
     // SANGNOM_B200_PREFETCH=0: no speculative next batch (every child frame is requested only when it is needed)
     prefetch_ = env_int("SANGNOM_B200_PREFETCH", 1, 0, 1) != 0;
+    // SANGNOM_B200_PIN_MB: budget for pinning the host's recycled frame buffers (0 = never). Unset: 2 GB, and only frame
+    // buffers of 16 MB and more are pinned - pinning costs ~4 ms per buffer whatever its size, once, which a few dozen
+    // large buffers repay (+5 % frames/s at 2160p fp32) and a few hundred small ones do not (+2 % at 1080p 8-bit
+    // after seconds of warm-up; profiles/README.md).
+    pin_min_bytes_ = std::getenv("SANGNOM_B200_PIN_MB") ? 0 : (size_t)16 << 20;
     pin_budget_ = (size_t)env_int("SANGNOM_B200_PIN_MB", 2048, 0, 1 << 20) << 20;
     if (sangnom_cuda_create(&cfg, &ctx_) != SN_OK)
         env->ThrowError("SangNom2: %s", sangnom_cuda_last_error(nullptr));
@@ -103,7 +108,7 @@ void SangNom2::note_frame_buffer(const PVideoFrame& f)
     VideoFrameBuffer* const vfb = f->GetFrameBuffer();
     const void* const base = vfb->GetReadPtr();
     const size_t bytes = (size_t)vfb->GetDataSize();
-    if (!base || bytes == 0 || bytes > pin_budget_) return;
+    if (!base || bytes == 0 || bytes > pin_budget_ || bytes < pin_min_bytes_) return;
     PinEntry& e = pins_[base];
     if (e.bytes != bytes) {                                 // a different buffer at an address seen before
         if (e.pinned) { sangnom_cuda_host_unpin(ctx_, const_cast<void*>(base)); pinned_bytes_ -= e.bytes; }
@@ -112,11 +117,14 @@ void SangNom2::note_frame_buffer(const PVideoFrame& f)
     }
     e.last_use = ++pin_clock_;
     if (e.pinned || ++e.seen < 2) return;                   // pinned already, or seen for the first time: may be a one-off
-    while (pinned_bytes_ + bytes > pin_budget_) {           // make room: unpin the least recently used buffer
+    while (pinned_bytes_ + bytes > pin_budget_) {           // make room: unpin the least recently used buffer ...
         auto lru = pins_.end();
         for (auto it = pins_.begin(); it != pins_.end(); ++it)
             if (it->second.pinned && (lru == pins_.end() || it->second.last_use < lru->second.last_use)) lru = it;
-        if (lru == pins_.end()) return;
+        // ... but only one that has dropped out of circulation (not touched for several batches). If every pinned
+        // buffer is still in use the working set simply does not fit the budget: this buffer stays pageable, rather
+        // than pinning and unpinning in turns (unpinning costs more than the staging copy it saves).
+        if (lru == pins_.end() || lru->second.last_use + 8ull * 2 * (uint64_t)batch_frames_ > pin_clock_) { --e.seen; return; }
         sangnom_cuda_host_unpin(ctx_, const_cast<void*>(lru->first));
         pinned_bytes_ -= lru->second.bytes;
         pins_.erase(lru);

@@ -71,3 +71,37 @@ def test_turn_planes_device(cuda, dtype, kind):
     for a, d in zip(srcs, d_dst):
         got = d.cpu().numpy().view(dtype)
         assert np.array_equal(got, [a.T, np.rot90(a, -1), np.rot90(a, 1)][kind])
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.float32], ids=["u8", "u16", "f32"])
+@pytest.mark.parametrize("kind", [0, 1, 2], ids=["transpose", "right", "left"])
+def test_turn_planes_ragged_sizes_through_tma(cuda, dtype, kind):
+    """Planes whose base and pitch are multiples of 16 bytes take the TMA kernel (sangnom_turn_tma.cuh) whatever their
+    size: tiles that stick out of the plane are zero-filled by the tensor-map load and clipped by the store, for the
+    flipped turns at NEGATIVE tile coordinates. Sizes here are deliberately not multiples of anything; the padding of
+    every row and the rows behind the plane must stay untouched."""
+    import torch
+    lib = cuda.load()
+    rng = np.random.default_rng(10 + kind)
+    sb = np.dtype(dtype).itemsize
+    shapes = [(77, 130), (200, 333), (1080, 1920), (65, 31), (1, 500), (300, 1), (129, 129)]
+    srcs, d_src, d_dst, planes = [], [], [], []
+    for (h, w) in shapes:
+        a = rng.integers(0, 255, size=(h, w)).astype(dtype)
+        sp = (w * sb + 15) // 16 * 16 + 16
+        dp = (h * sb + 15) // 16 * 16 + 32
+        s = torch.full((h, sp), 0x11, dtype=torch.uint8, device="cuda")
+        s[:, :w * sb] = torch.from_numpy(a.view(np.uint8).reshape(h, -1)).cuda()
+        d = torch.full((w + 2, dp), 0xEE, dtype=torch.uint8, device="cuda")       # two guard rows behind the plane
+        srcs.append(a); d_src.append(s); d_dst.append(d)
+        planes.append(cuda.SnTurnPlane(s.data_ptr(), sp, d.data_ptr(), dp, w, h))
+    arr = (cuda.SnTurnPlane * len(planes))(*planes)
+    torch.cuda.synchronize()
+    assert lib.sangnom_cuda_turn_planes_device(sb, kind, arr, len(planes), C.c_void_p(0)) == 0
+    torch.cuda.synchronize()
+    for a, d in zip(srcs, d_dst):
+        h, w = a.shape
+        full = d.cpu().numpy()
+        got = full[:w, :h * sb].copy().view(dtype)
+        assert np.array_equal(got, [a.T, np.rot90(a, -1), np.rot90(a, 1)][kind]), f"{a.shape}"
+        assert (full[:w, h * sb:] == 0xEE).all() and (full[w:] == 0xEE).all(), f"{a.shape}: wrote outside the plane"
