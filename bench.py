@@ -645,20 +645,13 @@ def plugin_fps(wl, seconds):
                 raise RuntimeError(err.value.decode())
             L.fh_frame_release(f)
 
-        # warm-up: at least 6 batches, then until a window of frames is no faster than the one before (pinning done), at most ~20 s
+        # warm-up: 16 of the plugin's batches (its default batch: about 512 MB of finished frames, 4..128), so that
+        # every recycled frame buffer has been seen twice (and pinned, where the plugin pins); at most ~25 s
+        frame_bytes = sum(int(np.prod(fmt.plane_shape(w, h, p))) for p in range(fmt.components)) * fmt.sample_bytes
+        batch = int(os.environ.get("SANGNOM_B200_BATCH", max(4, min(128, (512 << 20) // max(frame_bytes, 1)))))
         n, t_start = 0, time.perf_counter()
-        win = 64 if fmt.sample_bytes * w * h < (8 << 20) else 8
-        prev = None
-        while True:
-            t0 = time.perf_counter()
-            for _ in range(win):
-                pull(n); n += 1
-            rate = win / (time.perf_counter() - t0)
-            if n >= 6 * win and prev is not None and rate < 1.15 * prev:
-                break
-            if time.perf_counter() - t_start > 20:
-                break
-            prev = rate
+        while n < max(96, 16 * batch) and time.perf_counter() - t_start < 25:
+            pull(n); n += 1
         warm = n
         t0, n0 = time.perf_counter(), n
         while time.perf_counter() - t0 < seconds and n < total:

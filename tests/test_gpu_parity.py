@@ -261,3 +261,33 @@ def test_failed_batch_does_not_disturb_its_neighbours(cuda):
     for k in range(6):
         exp = O.oracle_frame(frames[k], fmt.bits, order=0, aa=48, aac=48, parity=parity_of(k))
         assert_planes_equal((o1 + o2)[k], exp[:3], f"frame {k}")
+
+
+@pytest.mark.parametrize("fmtname", ["YUV420P8", "YUV420P10", "YUV420PS"])
+def test_multi_device_context(cuda, fmtname):
+    """Several GPUs behind ONE context (sn_config.device_mask / SN_DEVICE_ALL): chunks of consecutive frames are dealt
+    round-robin to one pipeline per device; every frame still equals the oracle, whichever GPU it ran on. Needs two
+    GPUs (skipped on a one-GPU box; the chunk dealing itself is covered on the CPU by tests/test_sharding.py)."""
+    import torch
+    from oracle import oracle as O
+    from pysangnom.clips import make_frame
+    from pysangnom.formats import FORMATS
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ndev = min(torch.cuda.device_count(), 8)
+    fmt, w, h, nf = FORMATS[fmtname], 352, 288, 27
+    frames = [make_frame(71, w, h, fmt, "noise" if i % 2 else "edges", i) for i in range(nf)]
+    with cuda.Context(fmt.sample_bytes, w, h, device=list(range(ndev)), max_frames_in_flight=8) as ctx:     # chunks of 2 frames
+        assert ctx.device_count() == ndev
+        got = ctx.process_frames(frames, fmt.bits, order=0, aa=48, aac=48, parities=[parity_of(i) for i in range(nf)])
+        # a second batch continues the round-robin where the first one stopped
+        got2 = ctx.process_frames(frames[:5], fmt.bits, order=2, aa=48, aac=20)
+        assert ctx.stats()["frames"] == nf + 5
+    for i, fr in enumerate(frames):
+        exp = O.oracle_frame(fr, fmt.bits, order=0, aa=48, aac=48, parity=parity_of(i))
+        assert_planes_equal(got[i][:3], exp[:3], f"multi-device {fmtname} frame {i}")
+    for i, fr in enumerate(frames[:5]):
+        exp = O.oracle_frame(fr, fmt.bits, order=2, aa=48, aac=20)
+        assert_planes_equal(got2[i][:3], exp[:3], f"multi-device {fmtname} second batch frame {i}")
+    with cuda.Context(fmt.sample_bytes, w, h, device=cuda.DEVICE_ALL) as ctx:
+        assert ctx.device_count() == torch.cuda.device_count()

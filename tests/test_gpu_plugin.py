@@ -246,3 +246,19 @@ def test_prefetch_failure_does_not_fail_a_finished_frame(monkeypatch):
         src.fail_at(-1)
         for i in range(4, n):
             assert np.array_equal(flt.get_frame(i)[0], exp[i])
+
+
+def test_plugin_on_all_devices(monkeypatch):
+    """SANGNOM_B200_DEVICES=all: one filter instance, one pipeline per GPU. Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    monkeypatch.setenv("SANGNOM_B200_DEVICES", "all")
+    monkeypatch.setenv("SANGNOM_B200_BATCH", "8")
+    fmt = FORMATS["YUV420P8"]
+    w, h, n = 176, 144, 40
+    frames = [make_frame(15, w, h, fmt, "noise", i) for i in range(n)]
+    got = run_plugin(OURS, fmt, w, h, frames, dict(order=0, aa=48, aac=48))
+    for i, fr in enumerate(frames):
+        exp = O.oracle_frame(fr, 8, order=0, aa=48, aac=48, parity=parity_of(i))
+        assert_planes_equal(got[i][:3], exp[:3], f"all-devices frame {i}")
