@@ -268,7 +268,7 @@ static int chain_process_impl(sn_chain* ch, const sn_chain_job* jobs, int njobs)
         std::vector<sn::TurnPlane> tp((size_t)np);
         for (int i = 0; i < np; ++i) {
             const Place& p = pl[i];
-            tp[i] = sn::TurnPlane{ d1 + p.o1, (long long)p.p1, d2 + p.o2, (long long)p.p2, p.jb->width, 2 * p.jb->height };
+            tp[i] = sn::TurnPlane{ d1 + p.o1, (long long)p.p1, d2 + p.o2, (long long)p.p2, p.jb->width, 2 * p.jb->height, 1 };
         }
         int nl = 0;
         if ((e = sn::launch_turn_planes(sb, tp.data(), np, first_turn, ch->compute, &nl)) != cudaSuccess) {
@@ -289,7 +289,7 @@ static int chain_process_impl(sn_chain* ch, const sn_chain_job* jobs, int njobs)
         // ---- turn back: 2H x 2W -> 2W x 2H ----
         for (int i = 0; i < np; ++i) {
             const Place& p = pl[i];
-            tp[i] = sn::TurnPlane{ d3 + p.o3, (long long)p.p3, d_out + p.o_out, (long long)p.p_out, 2 * p.jb->height, 2 * p.jb->width };
+            tp[i] = sn::TurnPlane{ d3 + p.o3, (long long)p.p3, d_out + p.o_out, (long long)p.p_out, 2 * p.jb->height, 2 * p.jb->width, 1 };
         }
         ch->stats.kernel_launches += nl;
         if ((e = sn::launch_turn_planes(sb, tp.data(), np, second_turn, ch->compute, &nl)) != cudaSuccess) {
@@ -340,7 +340,7 @@ int sangnom_cuda_turn_planes_device(int sample_type, int kind, const sn_turn_pla
     if (nplanes == 0) return SN_OK;
     std::vector<sn::TurnPlane> tp((size_t)nplanes);
     for (int i = 0; i < nplanes; ++i)
-        tp[i] = sn::TurnPlane{ planes[i].src, (long long)planes[i].src_pitch, planes[i].dst, (long long)planes[i].dst_pitch, planes[i].width, planes[i].height };
+        tp[i] = sn::TurnPlane{ planes[i].src, (long long)planes[i].src_pitch, planes[i].dst, (long long)planes[i].dst_pitch, planes[i].width, planes[i].height, (planes[i].flags & SN_TURN_DST_PADDING_WRITABLE) ? 1 : 0 };
     const cudaError_t e = sn::launch_turn_planes(sample_type, tp.data(), nplanes, static_cast<sn::TurnKind>(kind), static_cast<cudaStream_t>(cuda_stream));
     if (e != cudaSuccess) { cudaGetLastError(); return SN_ERR_CUDA; }
     return SN_OK;

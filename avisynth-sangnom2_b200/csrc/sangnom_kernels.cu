@@ -262,7 +262,8 @@ cudaError_t launch_turn_planes(int sample_bytes, const TurnPlane* planes, int np
         // (a turn that mirrors the source columns tiles the plane from its right edge: the tile origins are multiples of
         // 16 bytes - which the tensor-map load needs of its inner coordinate - only if the row length is)
         const bool ok = !plain_only && encode_tiled() != nullptr && tma_addressable(p.src, p.src_pitch, p.width, p.height) &&
-                        tma_addressable(p.dst, p.dst_pitch, p.height, p.width) && (!fr || ((long long)p.width * sample_bytes) % 16 == 0);
+                        tma_addressable(p.dst, p.dst_pitch, p.height, p.width) && (!fr || ((long long)p.width * sample_bytes) % 16 == 0) &&
+                        (p.dst_padding_writable || ((long long)p.height * sample_bytes) % 16 == 0);
         (ok ? viaTma : plain).push_back(&p);
     }
     for (size_t first = 0; first < viaTma.size(); first += turn::kTmaMaxPlanes) {

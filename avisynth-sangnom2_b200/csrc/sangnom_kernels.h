@@ -75,6 +75,10 @@ struct TurnPlane {
     const void* src; long long src_pitch;   // W x H samples, pitch in bytes
     void* dst; long long dst_pitch;         // H x W samples
     int width, height;
+    // The bytes between the end of a dst row (height samples) and the next multiple of 16 may be overwritten (the
+    // tensor-map store of the TMA path clips at 16-byte granularity). The device chain's own planes say yes; planes of
+    // a caller who did not say so take the TMA path only when their rows are a whole number of 16-byte pieces.
+    int dst_padding_writable;
 };
 enum TurnKind { kTranspose = 0, kTurnRight = 1, kTurnLeft = 2 };
 // Asynchronous on `stream`; the plane table travels in the kernel parameters (64 planes per launch). Returns the

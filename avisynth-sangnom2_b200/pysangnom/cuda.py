@@ -31,6 +31,7 @@ EXPORTS = [
     "sangnom_cuda_host_pin", "sangnom_cuda_host_unpin", "sangnom_cuda_device_count",
 ]
 TURN_TRANSPOSE, TURN_RIGHT_LEFT, TURN_LEFT_RIGHT = range(3)
+TURN_DST_PADDING_WRITABLE = 1
 
 
 class SnConfig(C.Structure):
@@ -63,7 +64,7 @@ class SnChainStats(C.Structure):
 
 class SnTurnPlane(C.Structure):
     _fields_ = [("src", C.c_void_p), ("src_pitch", C.c_ssize_t), ("dst", C.c_void_p), ("dst_pitch", C.c_ssize_t),
-                ("width", C.c_int), ("height", C.c_int)]
+                ("width", C.c_int), ("height", C.c_int), ("flags", C.c_int)]
 
 
 class SnLimits(C.Structure):

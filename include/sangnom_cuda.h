@@ -239,10 +239,16 @@ SN_API const char* sangnom_cuda_chain_last_error(sn_chain* chain);
 
 /* The turn on its own, device planes: dst (height x width samples) = src (width x height) transposed (kind 0),
  * turned clockwise (1) or counter-clockwise (2). Asynchronous on `cuda_stream` (a cudaStream_t as void*). */
+/* sn_turn_plane.flags: the caller does not care about the bytes between the end of a dst row (`height` samples) and
+ * the next multiple of 16 bytes inside its pitch - they may be overwritten. Lets planes with any row length take the
+ * tensor-map (TMA) path, whose stores clip at 16-byte granularity; without it only planes whose dst rows are a whole
+ * number of 16-byte pieces do, the others take the plain kernel. */
+#define SN_TURN_DST_PADDING_WRITABLE 1
 typedef struct sn_turn_plane {
     const void* src; ptrdiff_t src_pitch;
     void* dst; ptrdiff_t dst_pitch;
     int width, height;        /* of src, in samples */
+    int flags;                /* SN_TURN_* bits */
 } sn_turn_plane;
 SN_API int sangnom_cuda_turn_planes_device(int sample_type, int kind, const sn_turn_plane* planes, int nplanes, void* cuda_stream);
 

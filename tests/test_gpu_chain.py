@@ -73,9 +73,10 @@ def test_turn_planes_device(cuda, dtype, kind):
         assert np.array_equal(got, [a.T, np.rot90(a, -1), np.rot90(a, 1)][kind])
 
 
+@pytest.mark.parametrize("pad_writable", [False, True], ids=["exact", "padding_writable"])
 @pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.float32], ids=["u8", "u16", "f32"])
 @pytest.mark.parametrize("kind", [0, 1, 2], ids=["transpose", "right", "left"])
-def test_turn_planes_ragged_sizes_through_tma(cuda, dtype, kind):
+def test_turn_planes_ragged_sizes_through_tma(cuda, dtype, kind, pad_writable):
     """Planes whose base and pitch are multiples of 16 bytes take the TMA kernel (sangnom_turn_tma.cuh) whatever their
     size: tiles that stick out of the plane are zero-filled by the tensor-map load and clipped by the store, for the
     flipped turns at NEGATIVE tile coordinates. Sizes here are deliberately not multiples of anything; the padding of
@@ -84,7 +85,9 @@ def test_turn_planes_ragged_sizes_through_tma(cuda, dtype, kind):
     lib = cuda.load()
     rng = np.random.default_rng(10 + kind)
     sb = np.dtype(dtype).itemsize
-    shapes = [(77, 130), (200, 333), (1080, 1920), (65, 31), (1, 500), (300, 1), (129, 129)]
+    # (rows, columns). The TMA path takes planes whose destination rows (= source rows, in bytes) are a multiple of 16
+    # and, for TurnLeft, whose source rows are too; the others exercise the plain kernel next to it in the same call.
+    shapes = [(80, 130), (208, 333), (1080, 1920), (64, 31), (16, 500), (304, 1), (144, 129), (77, 130), (1, 500)]
     srcs, d_src, d_dst, planes = [], [], [], []
     for (h, w) in shapes:
         a = rng.integers(0, 255, size=(h, w)).astype(dtype)
@@ -94,7 +97,7 @@ def test_turn_planes_ragged_sizes_through_tma(cuda, dtype, kind):
         s[:, :w * sb] = torch.from_numpy(a.view(np.uint8).reshape(h, -1)).cuda()
         d = torch.full((w + 2, dp), 0xEE, dtype=torch.uint8, device="cuda")       # two guard rows behind the plane
         srcs.append(a); d_src.append(s); d_dst.append(d)
-        planes.append(cuda.SnTurnPlane(s.data_ptr(), sp, d.data_ptr(), dp, w, h))
+        planes.append(cuda.SnTurnPlane(s.data_ptr(), sp, d.data_ptr(), dp, w, h, cuda.TURN_DST_PADDING_WRITABLE if pad_writable else 0))
     arr = (cuda.SnTurnPlane * len(planes))(*planes)
     torch.cuda.synchronize()
     assert lib.sangnom_cuda_turn_planes_device(sb, kind, arr, len(planes), C.c_void_p(0)) == 0
@@ -104,4 +107,6 @@ def test_turn_planes_ragged_sizes_through_tma(cuda, dtype, kind):
         full = d.cpu().numpy()
         got = full[:w, :h * sb].copy().view(dtype)
         assert np.array_equal(got, [a.T, np.rot90(a, -1), np.rot90(a, 1)][kind]), f"{a.shape}"
-        assert (full[:w, h * sb:] == 0xEE).all() and (full[w:] == 0xEE).all(), f"{a.shape}: wrote outside the plane"
+        # SN_TURN_DST_PADDING_WRITABLE: the bytes up to the next multiple of 16 of every row are the library's to overwrite
+        keep_from = (h * sb + 15) // 16 * 16 if pad_writable else h * sb
+        assert (full[:w, keep_from:] == 0xEE).all() and (full[w:] == 0xEE).all(), f"{a.shape}: wrote outside the plane"

@@ -12,7 +12,7 @@ for sb, w, h, n in ((2, 1920, 2160, 48), (2, 2160, 3840, 24), (1, 1920, 1080, 96
     sp, dp = (w * sb + 255) // 256 * 256, (h * sb + 255) // 256 * 256
     a = torch.randint(0, 255, (n, h, sp), dtype=torch.uint8, device="cuda")
     b = torch.empty((n, w, dp), dtype=torch.uint8, device="cuda")
-    planes = (cuda.SnTurnPlane * n)(*[cuda.SnTurnPlane(a[i].data_ptr(), sp, b[i].data_ptr(), dp, w, h) for i in range(n)])
+    planes = (cuda.SnTurnPlane * n)(*[cuda.SnTurnPlane(a[i].data_ptr(), sp, b[i].data_ptr(), dp, w, h, cuda.TURN_DST_PADDING_WRITABLE) for i in range(n)])
     stream = torch.cuda.Stream()
     for kind, name in ((0, "transpose"), (1, "turn_right"), (2, "turn_left")):
         for _ in range(3):
