@@ -316,6 +316,20 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
             else { Pb[i][0] = Pb[i][1] = Pb[i][2] = Pb[i][3] = I(0); }
         }
     };
+    // The same cells pulled towards L1 a row ahead of their use: threads without (all) pixel columns read the previous
+    // pass's cost state every row, and holding a row of it in registers across phase B (as the 8-bit kernel does) costs
+    // 36 registers this kernel does not have - it spilled. A prefetch costs none.
+    auto prefetch_stale = [&](int row) {
+#ifndef SN_HOST_EMULATION
+        const StateRow<T> in = state_row<T>(t.in, row, x0, S);
+        if (in.p != nullptr) {
+#pragma unroll
+            for (int i = 0; i < kNumCost; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(in.p + i * in.stride));
+        }
+#else
+        (void)row;
+#endif
+    };
     // Nine raw costs of the pair (upper row window u / 3-tap u3, lower row l / l3) for my columns; columns without
     // pixels keep what Pb holds (the straddling thread's stale costs).
     auto pair_costs = [&](auto full, const I (&u)[kWin], const Tap3& u3, const I (&l)[kWin], const Tap3& l3, I (&Pb)[kNumCost][kCols]) {
@@ -365,8 +379,8 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
 #pragma unroll
             for (int c = 0; c < kCols; ++c) M[i][c] = Pb[i][c];
     }
-    // Threads without (all) pixel columns read the cost state the previous pass handed over, one row ahead: sp holds
-    // pool row r+1 at the top of row r.
+    // Threads without (all) pixel columns read the cost state the previous pass handed over every row (prefetched a row
+    // ahead, see prefetch_stale).
 #ifdef SN_HOST_EMULATION
     bool warp_full = true, warp_edge = false;
     for (int l = wfirst; l <= wlast; ++l) {
@@ -378,8 +392,7 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
     const bool warp_full = __all_sync(0xFFFFFFFFu, npix == kCols);
     const bool warp_edge = __any_sync(0xFFFFFFFFu, edge);
 #endif
-    I sp[kNumCost][kCols];
-    if (!warp_full) stale_costs(2, sp);
+    if (!warp_full) prefetch_stale(2);
     // all blocks of a cluster run, with their halo barriers initialised, before the first DSMEM store
     if constexpr (kClustered) {
         if (threadIdx.x == 0) {
@@ -420,14 +433,7 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
         I own0[4];                                                                        // my own L values of the first cost visited in phase B
         {
             I Pb[kNumCost][kCols];
-            if constexpr (!kFull) {
-#pragma unroll
-                for (int i = 0; i < kNumCost; ++i)
-#pragma unroll
-                    for (int c = 0; c < kCols; ++c) Pb[i][c] = sp[i][c];
-            } else if constexpr (!kPair) {
-                stale_costs(r + 1, Pb);
-            }
+            if constexpr (!kFull || !kPair) stale_costs(r + 1, Pb);
             if (kPair && pixels) {
                 I wb[kWin], wc[kWin];
                 Tap3 tb, tc;
@@ -477,7 +483,7 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
             if (seg_first && !plane_first) cl::halo_wait(halo_bar(0, r & 1), halo_parity, kNumCost * 16u);
             if (right_block) cl::halo_wait(halo_bar(1, r & 1), halo_parity, kNumCost * 16u);
         }
-        if constexpr (!kFull) stale_costs(r + 2, sp);       // next row's handed-over state: in flight during phase B
+        if constexpr (!kFull) prefetch_stale(r + 2);        // next row's handed-over state: on its way during phase B
 
         // ---- per cost: 7-tap sum, B = narrowT(sum / 16), min key, M = P[r+1] + B ----
         int kmin[kCols];        // integer flavours: min over (B << 4 | rank) keys, threshold folded in as a tenth key
