@@ -69,11 +69,16 @@ SangNom2::SangNom2(PClip _child, int order, int aa, int aac, int threads, bool d
     cfg.pool_width = vi.width;       // pool geometry comes from the OUTPUT luma size (:287-288)
     cfg.pool_height = vi.height;
     // frames fetched and processed per cache miss on sequential access: enough to keep the device pipeline busy, but
-    // bounded by the memory the finished frames occupy until they are served (about 512 MB per batch by default)
+    // bounded by the memory the finished frames occupy until they are served (about 1 GB per batch by default)
     const long long frame_bytes = (long long)vi.width * vi.height * sample_bytes_ * (plane_count_ == 1 ? 2 : 3) / 2 + 1;
-    const int default_batch = (int)std::max(4LL, std::min(128LL, (512LL << 20) / frame_bytes));
+    const int default_batch = (int)std::max(4LL, std::min(128LL, (1024LL << 20) / frame_bytes));
     batch_frames_ = env_int("SANGNOM_B200_BATCH", default_batch, 1, 256);
-    cfg.max_frames_in_flight = batch_frames_ < 3 ? 3 : batch_frames_;
+    // A batch is cut into four chunks (the library keeps four chunks in flight per GPU: host copies | H2D | kernels |
+    // D2H). Smaller chunks lose: a chunk's kernels take about as long for 4 frames as for 40 (the row sweep is a chain
+    // of H/2 dependent steps, frames only add blocks beside it), so fewer frames per chunk is fewer frames per unit of
+    // kernel latency - measured 13.4k / 11.9k / 10.0k / 6.7k frames/s at 1080p for 4 / 8 / 16 / 32 chunks per batch;
+    // larger ones (2 or 1 chunk per batch) stop overlapping the stages: 11.2k / 8.1k. SANGNOM_B200_INFLIGHT overrides.
+    cfg.max_frames_in_flight = env_int("SANGNOM_B200_INFLIGHT", 4 * ((batch_frames_ + 3) / 4), 1, 4096);
     // SANGNOM_B200_PERSISTENT=1: keep the scratch-pool state from frame to frame like one long-lived reference
     // instance (bit-compatible with a sequential single-instance reference run where that is not frame-pure:
     // widths that are not a multiple of 32, luma=false with subsampled chroma). Frames then run one after another.

@@ -685,10 +685,10 @@ def plugin_fps(wl, seconds):
                 raise RuntimeError(err.value.decode())
             L.fh_frame_release(f)
 
-        # warm-up: 16 of the plugin's batches (its default batch: about 512 MB of finished frames, 4..128), so that
+        # warm-up: 16 of the plugin's batches (its default batch: about 1 GB of finished frames, 4..128), so that
         # every recycled frame buffer has been seen twice (and pinned, where the plugin pins); at most ~25 s
         frame_bytes = sum(int(np.prod(fmt.plane_shape(w, h, p))) for p in range(fmt.components)) * fmt.sample_bytes
-        batch = int(os.environ.get("SANGNOM_B200_BATCH", max(4, min(128, (512 << 20) // max(frame_bytes, 1)))))
+        batch = int(os.environ.get("SANGNOM_B200_BATCH", max(4, min(128, (1024 << 20) // max(frame_bytes, 1)))))
         n, t_start = 0, time.perf_counter()
         while n < max(96, 16 * batch) and time.perf_counter() - t_start < 25:
             pull(n); n += 1
