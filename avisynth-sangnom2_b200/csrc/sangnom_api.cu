@@ -306,13 +306,14 @@ int sangnom_cuda_create(const sn_config* cfg, sn_ctx** out)
     if (cfg->max_frames_in_flight > 0) {
         ctx->frames_in_flight = cfg->max_frames_in_flight;
     } else {
-        // default: one frame per SM over the kSlots chunks in flight - chunks small enough that the pipeline's
-        // ramp (first upload, last download, one kernel latency) stays short, large enough that the chunks whose
-        // kernels overlap fill the GPU - capped at ~24 GB of device memory per device (kept rows, interpolated rows
-        // and cost state: about 1.5 x the three planes of a frame)
-        const double per_frame = 1.5 * 3.0 * (double)S * (double)cfg->pool_height * (double)cfg->sample_type;
-        const long long fit = (long long)(24.0e9 / per_frame);
-        ctx->frames_in_flight = (int)std::min<long long>(prop.multiProcessorCount, std::max<long long>(fit, 12));
+        // default: one frame per SM over the kSlots chunks in flight - chunks small enough that the pipeline's ramp
+        // (first upload, last download, one kernel latency) stays short, large enough that the chunks whose kernels
+        // overlap fill the GPU - and at most about 512 MB of planes per chunk, so that a batch of large frames still
+        // makes enough chunks to overlap the stages and to go round several devices
+        const double frame_bytes = 1.5 * (double)S * (double)cfg->pool_height * (double)cfg->sample_type;      // 4:2:0-sized estimate
+        const long long by_bytes = std::max<long long>(1, (long long)(512.0e6 / frame_bytes));
+        const long long chunk = std::min<long long>(std::max(1, prop.multiProcessorCount / kSlots), by_bytes);
+        ctx->frames_in_flight = (int)(chunk * kSlots);
     }
     auto bail = [&](cudaError_t err, const char* what) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
@@ -323,7 +324,7 @@ int sangnom_cuda_create(const sn_config* cfg, sn_ctx** out)
     int copy_threads = cfg->copy_threads;
     if (copy_threads <= 0) {
         const char* v = getenv("SANGNOM_B200_COPY_THREADS");
-        copy_threads = v && *v ? atoi(v) : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+        copy_threads = v && *v ? atoi(v) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency() / 2));
     }
     copy_threads = std::max(1, std::min(copy_threads, 64));
     const int per_pipeline = std::max(1, copy_threads / (int)devices.size());
