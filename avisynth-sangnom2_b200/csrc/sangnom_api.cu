@@ -73,7 +73,7 @@ int plan_frames(sn_ctx* ctx, const sn_plane_job* jobs, int njobs, bool device_en
         sn::PassGeometry geo[3];
         for (int q = 0; q < m; ++q) { geo[q] = sn::PassGeometry{}; geo[q].width = f.passes[q].W; geo[q].kept_rows = f.passes[q].n; }
         f.state_bytes = sn::plan_frame_passes(geo, m, ctx->S, ctx->Hb, sb, ctx->persistent);
-        for (int q = 0; q < m; ++q) { f.passes[q].R = geo[q].sweep_rows; f.passes[q].cone = geo[q].cone; f.passes[q].in = geo[q].in; f.passes[q].out = geo[q].out; }
+        for (int q = 0; q < m; ++q) { f.passes[q].R = geo[q].sweep_rows; f.passes[q].cone = geo[q].cone; f.passes[q].export_cone = geo[q].export_cone; f.passes[q].in = geo[q].in; f.passes[q].out = geo[q].out; }
     }
     return SN_OK;
 }
@@ -122,7 +122,7 @@ sn::PlaneTask make_task(const sn_ctx* ctx, const Pass& p, void* plane, size_t pi
         t.no_border = copy_kept ? 0 : 1;
     }
     t.width = p.W; t.height = p.H; t.offset = p.job->offset;
-    t.kept_rows = p.n; t.sweep_rows = p.R; t.cone = p.cone;
+    t.kept_rows = p.n; t.sweep_rows = p.R; t.cone = p.cone; t.export_cone = p.export_cone;
     t.thr_f = p.job->threshold;
     // `const T aaf` (reference SangNom2.cpp:162,272): float -> T for integer samples. Truncate
     // toward zero, then wrap to the container width - what x86-64 does for the (undefined in C++)

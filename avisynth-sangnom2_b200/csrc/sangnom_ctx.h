@@ -64,7 +64,7 @@ struct Pass {
     const sn_plane_job* job = nullptr;
     int W = 0, H = 0, n = 0;     // samples, rows, kept rows
     int R = 0;                   // pool rows to sweep
-    int cone = 0;                // dependency-cone bound (sangnom_plan.h)
+    int cone = 0, export_cone = 0;   // dependency-cone bounds (sangnom_plan.h)
     sn::CostState in{}, out{};
     // host path: how the kept rows get up and the interpolated rows get down
     //   STAGED  pageable host memory: the pipeline's copy pool packs / scatters rows through the slot's pinned staging,

@@ -41,6 +41,8 @@ struct PlaneTask {
     int cone;               // dependency cone of everything downstream of this pass (sangnom_plan.h): at pool row r only the
                             // columns < cone - 3r can still reach a picture sample of this or a later pass of the frame;
                             // threads beyond it have nothing left to do. kNoCone: sweep everything (persistent pool).
+    int export_cone;        // the same bound for what the NEXT pass of the frame reads of this pass's blurred rows: row r is
+                            // handed over only by the threads whose first column is below export_cone - 3r
     CostState in, out;      // cost state from the previous pass / for the next pass of this frame
 };
 constexpr int kNoCone = 1 << 29;

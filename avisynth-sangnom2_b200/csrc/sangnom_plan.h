@@ -30,6 +30,7 @@ struct PassGeometry {
     int kept_rows;    // n = H/2
     int sweep_rows;   // out: R
     int cone;         // out: see PlaneTask::cone
+    int export_cone;  // out: see PlaneTask::export_cone
     CostState in, out;   // out: regions; pointers hold (byte offset + 1) into the frame's state scratch, 0 = empty
 };
 
@@ -55,6 +56,8 @@ inline size_t plan_frame_passes(PassGeometry* passes, int m, int S, int Hb, int 
         p.cone = p.width + 3 * p.kept_rows;
         if (q + 1 < m) p.cone = std::max(p.cone, passes[q + 1].cone + 6);
         if (persistent) p.cone = kNoCone;
+        // what pass q+1 reads of row r: the stale input of the rows it computes at r-1 and r, 3 columns beyond each
+        p.export_cone = (q + 1 < m && !persistent) ? passes[q + 1].cone + 3 : kNoCone;
     }
     size_t off = 0;
     for (int q = 0; q + 1 < m; ++q) {

@@ -599,7 +599,7 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
     auto export_row = [&](int r, StateRow<T>& out) -> bool {
         out = StateRow<T>{ nullptr, 0 };
         if (!((r >= ex_b0 && r <= ex_b1) || r <= ex_a1)) return false;
-        out = state_row<T>(t.out, r, x0, S);
+        if (x0 < t.export_cone - 3 * r) out = state_row<T>(t.out, r, x0, S);      // beyond it nothing downstream reads the row
         return true;
     };
     auto sweep = [&](auto full) {

@@ -47,7 +47,7 @@ int emul_frame(int sample_bytes, int nplanes, void* const* planes, const long lo
             t.copy_kept = 0;
         }
         t.width = widths[q]; t.height = heights[q]; t.offset = offsets[q];
-        t.kept_rows = geo[q].kept_rows; t.sweep_rows = geo[q].sweep_rows; t.cone = geo[q].cone;
+        t.kept_rows = geo[q].kept_rows; t.sweep_rows = geo[q].sweep_rows; t.cone = geo[q].cone; t.export_cone = geo[q].export_cone;
         t.thr_f = thresholds[q];
         t.thr_i = sample_bytes == 1 ? ((int)thresholds[q] & 0xFF) : ((int)thresholds[q] & 0xFFFF);
         t.in = geo[q].in; t.out = geo[q].out;
