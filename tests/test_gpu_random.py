@@ -20,6 +20,8 @@ from pysangnom.formats import FORMATS
 pytestmark = pytest.mark.gpu
 
 FMTS = ["Y8", "YV12", "YV16", "YV24", "YV411", "Y10", "YUV420P10", "YUV422P16", "YUV444P16", "Y32", "YUV420PS", "YUV444PS"]
+# SANGNOM_RANDOM_EXAMPLES=N: a longer, differently seeded soak (the default run is derandomised so that it repeats)
+_N = int(os.environ.get("SANGNOM_RANDOM_EXAMPLES", "0"))
 
 
 @pytest.fixture(scope="module")
@@ -41,7 +43,7 @@ def dev_plane(a, skew, extra, fill=None):
     return buf, view, pitch
 
 
-@settings(max_examples=70, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@settings(max_examples=_N or 70, deadline=None, derandomize=not _N, suppress_health_check=list(HealthCheck))
 @given(fmtname=st.sampled_from(FMTS), wq=st.integers(2, 180), h2=st.integers(1, 14), order=st.integers(0, 2),
        aa=st.integers(0, 128), aac=st.integers(0, 128), dh=st.booleans(), luma=st.booleans(), chroma=st.booleans(),
        seed=st.integers(0, 2 ** 16), kind=st.sampled_from(["noise", "edges"]), skew=st.sampled_from([0, 0, 1, 3, 8]),
@@ -93,7 +95,7 @@ def test_random_geometry_device_entry(cuda, fmtname, wq, h2, order, aa, aac, dh,
             os.environ.pop(name, None)
 
 
-@settings(max_examples=25, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@settings(max_examples=(_N // 3) or 25, deadline=None, derandomize=not _N, suppress_health_check=list(HealthCheck))
 @given(fmtname=st.sampled_from(["YV12", "YV411", "YUV420P10", "YUV420PS", "YV24", "Y8"]), wq=st.integers(66, 300), h2=st.integers(2, 10),
        order=st.integers(0, 2), seed=st.integers(0, 2 ** 16), pinned=st.booleans(), pad=st.sampled_from([0, 0, 3, 16]))
 def test_random_geometry_host_entry_clustered(cuda, fmtname, wq, h2, order, seed, pinned, pad):
