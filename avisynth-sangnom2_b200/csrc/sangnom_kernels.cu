@@ -1,13 +1,12 @@
-// Kernel launchers of libsangnom_cuda (sm_100a). The kernels themselves live in
-//   sangnom_u8.cuh    8-bit samples: packed 16-bit-lane arithmetic, 8 columns per thread
-//   sangnom_wide.cuh  16-bit and fp32 samples: one pixel per lane, 4 columns per thread
+// Kernel launchers of libsangnom_cuda (sm_100a). The row-sweep kernels live in
+//   sangnom_u8.cuh    8-bit samples: packed 16-bit-lane arithmetic, 8 columns per thread   (compiled in sangnom_kernels_u8.cu)
+//   sangnom_wide.cuh  16-bit and fp32 samples: one pixel per lane, 4 columns per thread    (sangnom_kernels_u16.cu, _f32.cu)
 // Both fuse the reference's three stages (/root/reference/src/SangNom2.cpp prepareBuffers_c :74-124,
 // processBuffers_c :126-159, finalizePlane_c :161-257) into one sweep down the pool rows so that the
 // nine cost buffers never exist in memory, and both split a plane that is too wide for one block
 // over the blocks of a thread-block cluster (sangnom_cluster.cuh).
 #include "sangnom_kernels.h"
-#include "sangnom_u8.cuh"
-#include "sangnom_wide.cuh"
+#include "sangnom_launch.h"
 #include "sangnom_turn.cuh"
 #include "sangnom_turn_tma.cuh"
 
@@ -19,136 +18,14 @@
 
 namespace sn {
 
-namespace {
-
-int env_int(const char* name, int def)
-{
-    const char* v = getenv(name);
-    return v && *v ? atoi(v) : def;
-}
-
-// Opt a kernel into `smem` bytes of dynamic shared memory once per device.
-template <typename K>
-cudaError_t ensure_smem(K kernel, size_t smem, size_t (&configured)[64])
-{
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= 64 || smem > configured[dev]) {
-        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) configured[dev] = smem;
-    }
-    return cudaSuccess;
-}
-
-template <typename K, typename... Args>
-cudaError_t launch_clustered(K kernel, int blocks, int threads, size_t smem, int cluster, cudaStream_t stream, Args... args)
-{
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)blocks);
-    cfg.blockDim = dim3((unsigned)threads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr{};
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = (unsigned)cluster;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = cluster > 1 ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kernel, args...);
-}
-
-// Split of a pool row over the blocks of a cluster: the smallest power of two (<= 8 blocks) that brings a segment down
-// to seg_pref columns with whole threads (cols_per_thread columns each); if that does not exist, the largest split
-// whose segments are whole threads and fit a block (seg_hard). 0 = this pool width cannot run.
-int cluster_split(int S, int seg_pref, int seg_hard, int cols_per_thread)
-{
-    int fallback = 0;
-    for (int G = 1; G <= 8; G *= 2) {
-        if (S % G != 0 || (S / G) % cols_per_thread != 0 || S / G > seg_hard) continue;
-        if (S / G <= seg_pref) return G;
-        fallback = G;
-    }
-    return fallback;
-}
-
-// One instantiation per (split over a cluster?, arithmetic flavour, spare threads?); shared-memory opt-in remembered per device.
-template <bool kClustered, bool kSat, bool kSpare>
-cudaError_t launch_u8_variant(const PlaneTask* tasks, int ntasks, LaunchGeometry g, int G, int seg, cudaStream_t stream)
-{
-    static size_t configured[64] = {};
-    auto kernel = u8k::sangnom_u8_row_sweep<256, 2, kClustered, kSat, kSpare>;
-    const size_t smem = u8k::smem_bytes(seg);
-    cudaError_t e = ensure_smem(kernel, smem, configured);
-    if (e != cudaSuccess) return e;
-    // kSpare: spare threads up to a whole number of warps plus one warp (at most 256); the kernel leaves the first few
-    // idle so that the last pixel thread ends a warp and the state-only threads start the next one (sangnom_u8.cuh)
-    const int T = seg / u8k::kCols;
-    const int threads = kSpare ? std::max(T, std::min(256, ((T + 31) & ~31) + 32)) : T;
-    return launch_clustered(kernel, ntasks * G, threads, smem, G, stream, tasks, g, seg);
-}
-
-// 8-bit: 8 columns per thread, at most 2048 columns per block.
-cudaError_t launch_u8(const PlaneTask* tasks, int ntasks, LaunchGeometry g, cudaStream_t stream)
-{
-    const int seg_max = std::min(std::max(env_int("SANGNOM_U8_SEG", 2048), 256), 2048);     // tuning / test knob, read per launch: small values force cluster splits at small sizes
-    const int G = cluster_split(g.S, seg_max, 2048, u8k::kCols);
-    if (G == 0) return cudaErrorInvalidValue;
-    const int seg = g.S / G;
-    if (G == 1) {
-        if (g.narrow && seg / u8k::kCols < 256)
-            return g.saturate ? launch_u8_variant<false, true, true>(tasks, ntasks, g, G, seg, stream) : launch_u8_variant<false, false, true>(tasks, ntasks, g, G, seg, stream);
-        return g.saturate ? launch_u8_variant<false, true, false>(tasks, ntasks, g, G, seg, stream) : launch_u8_variant<false, false, false>(tasks, ntasks, g, G, seg, stream);
-    }
-    return g.saturate ? launch_u8_variant<true, true, false>(tasks, ntasks, g, G, seg, stream) : launch_u8_variant<true, false, false>(tasks, ntasks, g, G, seg, stream);
-}
-
-template <typename T, bool kClustered, bool kSat, bool kSpare>
-cudaError_t launch_wide_variant(const PlaneTask* tasks, int ntasks, LaunchGeometry g, int G, int seg, cudaStream_t stream)
-{
-    static size_t configured[64] = {};
-    auto kernel = wide::sangnom_wide_row_sweep<T, 256, 2, kClustered, kSat, kSpare>;
-    const size_t smem = wide::smem_bytes<T>(seg);
-    cudaError_t e = ensure_smem(kernel, smem, configured);
-    if (e != cudaSuccess) return e;
-    // kSpare: as for the 8-bit kernel - spare threads so that the last pixel thread of a narrow plane ends a warp
-    const int T_ = seg / wide::kCols;
-    const int threads = kSpare ? std::max(T_, std::min(256, ((T_ + 31) & ~31) + 32)) : T_;
-    return launch_clustered(kernel, ntasks * G, threads, smem, G, stream, tasks, g, seg);
-}
-
-// 16-bit / fp32: 4 columns per thread, at most 1024 columns per block. fp32 has one flavour (the SSE2 path computes the
-// same floats).
-template <typename T>
-cudaError_t launch_wide(const PlaneTask* tasks, int ntasks, LaunchGeometry g, cudaStream_t stream)
-{
-    const int seg_max = std::min(std::max(env_int("SANGNOM_WIDE_SEG", 512), 128), 1024);   // tuning / test knob, read per launch
-    const int G = cluster_split(g.S, seg_max, 1024, wide::kCols);
-    if (G == 0) return cudaErrorInvalidValue;
-    const int seg = g.S / G;
-    constexpr bool kInt = !Flavour<T>::kFloat;
-    g.key_mask = (unsigned)Flavour<T>::kMask << 4;                  // the key mask of the integer flavour (sangnom_wide.cuh)
-    const bool spare = G == 1 && g.narrow && seg / wide::kCols < 256;
-    if constexpr (kInt) {
-        if (g.saturate) {
-            if (G != 1) return launch_wide_variant<T, true, true, false>(tasks, ntasks, g, G, seg, stream);
-            return spare ? launch_wide_variant<T, false, true, true>(tasks, ntasks, g, G, seg, stream) : launch_wide_variant<T, false, true, false>(tasks, ntasks, g, G, seg, stream);
-        }
-    }
-    if (G != 1) return launch_wide_variant<T, true, false, false>(tasks, ntasks, g, G, seg, stream);
-    return spare ? launch_wide_variant<T, false, false, true>(tasks, ntasks, g, G, seg, stream) : launch_wide_variant<T, false, false, false>(tasks, ntasks, g, G, seg, stream);
-}
-
-}  // namespace
+using namespace launch;
 
 int max_pool_width(int sample_bytes) { return sample_bytes == 1 ? 8 * 2048 : 8 * 1024; }
 
 bool pool_width_supported(int sample_bytes, int S)
 {
     if (S <= 0 || S % 32 != 0 || S > max_pool_width(sample_bytes)) return false;
-    return sample_bytes == 1 ? cluster_split(S, 2048, 2048, u8k::kCols) != 0 : cluster_split(S, 1024, 1024, wide::kCols) != 0;
+    return sample_bytes == 1 ? u8_width_supported(S) : wide_width_supported(S);
 }
 
 const char* kernel_variant_name(int sample_bytes, int S)
@@ -300,8 +177,8 @@ cudaError_t launch_plane_tasks(int sample_bytes, const PlaneTask* tasks_dev, int
     if (g.S % 32 != 0 || g.S > max_pool_width(sample_bytes)) return cudaErrorInvalidValue;
     switch (sample_bytes) {
         case 1: return launch_u8(tasks_dev, ntasks, g, stream);
-        case 2: return launch_wide<uint16_t>(tasks_dev, ntasks, g, stream);
-        case 4: return launch_wide<float>(tasks_dev, ntasks, g, stream);
+        case 2: return launch_u16(tasks_dev, ntasks, g, stream);
+        case 4: return launch_f32(tasks_dev, ntasks, g, stream);
         default: return cudaErrorInvalidValue;
     }
 }

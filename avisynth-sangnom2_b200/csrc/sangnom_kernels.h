@@ -1,4 +1,4 @@
-// Internal interface between the C-ABI layer (sangnom_api.cu) and the kernels (sangnom_kernels.cu).
+// Internal interface between the C-ABI layer (sangnom_api.cu) and the kernels (sangnom_kernels.cu and the per-flavour sangnom_kernels_*.cu).
 #pragma once
 #ifndef SN_HOST_EMULATION
 #include <cuda_runtime.h>

@@ -24,6 +24,8 @@ inline void mbar_wait(Mbar* b, unsigned parity)
 {
     while ((__atomic_load_n(&b->v, __ATOMIC_ACQUIRE) & 1u) == parity) std::this_thread::yield();
 }
+inline void fence_generic_to_async() {}
+
 #else
 struct __align__(8) Mbar { unsigned long long v; };
 
@@ -46,6 +48,9 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsi
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_addr(smem_dst)), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
 }
+// order this thread's ordinary shared-memory stores before later bulk copies into the same bytes (issued by another
+// thread after a block barrier)
+__device__ __forceinline__ void fence_generic_to_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(Mbar* b, unsigned parity)
 {
     const uint32_t bar = smem_addr(b);

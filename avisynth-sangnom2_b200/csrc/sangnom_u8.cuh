@@ -50,6 +50,9 @@ __device__ __forceinline__ constexpr uint32_t rank2(int i) { return rank1(i) * 0
 // what (key >> 4) leaks from the upper lane's rank nibble into the lower lane
 __device__ __forceinline__ constexpr uint32_t leak(int i) { return rank1(i) << 12; }
 
+// a value the compiler cannot see through: what is computed from it stays where it is written (no hoisting of a
+// cold path's loop-invariant arithmetic into the hot loop)
+__device__ __forceinline__ int opaque(int v) { asm volatile("" : "+r"(v)); return v; }
 __device__ __forceinline__ uint32_t fsr(uint32_t lo, uint32_t hi, int bytes) { return __funnelshift_r(lo, hi, bytes * 8); }
 __device__ __forceinline__ uint32_t lanes_lo(uint32_t w) { return __byte_perm(w, 0, 0x4140); }   // bytes 0,1 -> two u16 lanes
 __device__ __forceinline__ uint32_t lanes_hi(uint32_t w) { return __byte_perm(w, 0, 0x4342); }   // bytes 2,3 -> two u16 lanes
@@ -170,25 +173,6 @@ __device__ __forceinline__ uint2 interpolate8(const Taps& c, const Tap3& c3, con
     return out;
 }
 
-// Replicate the picture edges inside a window of bytes x0-4 .. x0+11 (reference loadPixel :25-34).
-__device__ __forceinline__ void fix_edges(uint32_t (&w)[4], int x0, int W)
-{
-    if (x0 == 0) w[0] = (w[1] & 0xFFu) * 0x01010101u;
-    if (x0 + 11 > W - 1) {                       // right edge inside this window: replicate pixel W-1
-        const int e = W - 1 - (x0 - 4);          // window byte index of the last picture pixel (>= 4)
-        uint32_t ev = 0;
-#pragma unroll
-        for (int i = 1; i < 4; ++i) if ((e >> 2) == i) ev = (w[i] >> (8 * (e & 3))) & 0xFFu;
-        ev *= 0x01010101u;
-#pragma unroll
-        for (int i = 1; i < 4; ++i) {
-            const int first = 4 * i;             // window byte index of this word's byte 0
-            if (e < first) w[i] = ev;
-            else if (e < first + 3) { const uint32_t keep = 0xFFFFFFFFu >> (8 * (3 - (e - first))); w[i] = (w[i] & keep) | (ev & ~keep); }
-        }
-    }
-}
-
 // Where the cost state of one pool row lives for this thread's 8 columns: bytes of buffer i at p + i * stride.
 // p == nullptr: outside the handed-over regions (reads as the zero-filled pool, nothing to write).
 struct StateRow { uint8_t* p; size_t stride; };
@@ -260,13 +244,14 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     // halo barriers, 16 bytes apart: [side 0 = left, 1 = right][row parity]
     unsigned char* const halo_raw = reinterpret_cast<unsigned char*>(mbar + kRing);
     auto halo_bar = [&](int side, int par) -> cl::HaloBar* { return reinterpret_cast<cl::HaloBar*>(halo_raw + (side * 2 + par) * 16); };
+    unsigned char* const task_raw = halo_raw + 4 * 16;
     {
-        uint32_t* const dst = reinterpret_cast<uint32_t*>(halo_raw + 4 * 16);
+        uint32_t* const dst = reinterpret_cast<uint32_t*>(task_raw);
         const uint32_t* const from = reinterpret_cast<const uint32_t*>(tasks + blockIdx.x / G);
         for (unsigned k = threadIdx.x; k < sizeof(PlaneTask) / 4; k += blockDim.x) dst[k] = from[k];
         __syncthreads();
     }
-    const PlaneTask& t = *reinterpret_cast<const PlaneTask*>(halo_raw + 4 * 16);
+    const PlaneTask& t = *reinterpret_cast<const PlaneTask*>(task_raw);
 
     const int W = t.width, n = t.kept_rows, R = t.sweep_rows;
     const int seg_x0 = (int)crank * seg_cols;
@@ -300,7 +285,12 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     const int wpad = (W + 15) & ~15;
     // which of my 8 columns carry pixels: all, none, or a prefix (the one thread that straddles W)
     const int npix = min(max(W - x0, 0), kCols);
-    const bool edge = npix > 0 && (x0 == 0 || x0 + 11 > W - 1);
+    // Picture edges (reference loadPixel :25-34: pixel 0 and pixel W-1 replicated outwards) are made in the staged rows
+    // themselves, once per kept row, by one thread each - not in every window that touches them (three per pool row):
+    // the block that holds pool column 0 fills positions -4..-1, the block(s) with a pixel thread whose window reaches
+    // past W-1 fill W..W+10. Done two rows ahead of a row's first use, so the row barrier in between publishes it.
+    const bool patch_left = seg_x0 == 0 && tid == 0 && W > 0;
+    const bool patch_right = seg_x0 < W && W <= seg_x0 + seg_cols + 3 && tid == min(T - 1, (W - 1 - seg_x0) / kCols);
     const bool vec_out = ((reinterpret_cast<uintptr_t>(t.plane) | (uintptr_t)t.pitch) & 7) == 0 && npix == kCols;   // aligned 8-byte stores
 
 
@@ -319,9 +309,10 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     // cooperative mode (unaligned sources): my own 8 bytes of a row, edge threads also the neighbour segments' halo
     auto coop_load = [&](int j, uint2 (&v)[3]) {
         const uint8_t* row = kept_row(j);
-        v[0] = load8_guarded(row, x0, W, fast8);
-        if (kClustered && seg_first) v[1] = load8_guarded(row, x0 - 8, W, fast8);
-        if (kClustered && seg_last) v[2] = load8_guarded(row, x0 + 8, W, fast8);
+        const int xo = opaque(x0);      // keeps this rare path's address arithmetic inside its branch, out of every row's head
+        v[0] = load8_guarded(row, xo, W, fast8);
+        if (kClustered && seg_first) v[1] = load8_guarded(row, xo - 8, W, fast8);
+        if (kClustered && seg_last) v[2] = load8_guarded(row, xo + 8, W, fast8);
     };
     auto coop_store = [&](int j, const uint2 (&v)[3]) {
         uint8_t* s = slot_of(j) + kRingPad + lx;
@@ -338,7 +329,17 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
         const uint2 own = *reinterpret_cast<const uint2*>(s);
         w[1] = own.x; w[2] = own.y;
         w[3] = *reinterpret_cast<const uint32_t*>(s + 8);
-        if (edge) fix_edges(w, x0, W);
+    };
+    // the edge replication of staged row j (the caller has seen the row land)
+    auto patch_row = [&](int j) {
+        uint8_t* const s = slot_of(j) + kRingPad - seg_x0;        // row position p lives at s[p]
+        if (patch_left) *reinterpret_cast<uint32_t*>(s - 4) = (uint32_t)s[0] * 0x01010101u;
+        if (patch_right) {
+            const uint8_t e = s[W - 1];
+#pragma unroll
+            for (int k = 0; k < 11; ++k) s[W + k] = e;
+        }
+        stage::fence_generic_to_async();                          // the slot's next bulk copy overwrites these bytes
     };
     auto t3_put = [&](int j, const Tap3& v) { t3ring[(size_t)(j & (kT3Ring - 1)) * T + tid] = make_uint4(v.f[0], v.f[1], v.b[0], v.b[1]); };
     auto t3_get = [&](int j, Tap3& v) { const uint4 q = t3ring[(size_t)(j & (kT3Ring - 1)) * T + tid]; v.f[0] = q.x; v.f[1] = q.y; v.b[0] = q.z; v.b[1] = q.w; };
@@ -366,6 +367,12 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
             if (kAhead < n) coop_load(kAhead, pre);
             __syncthreads();
         }
+    }
+
+    if (seg_has_pixels) {
+        if (patch_left || patch_right)
+            for (int j = 0; j < 3 && j < n; ++j) { await_row(j); patch_row(j); }
+        __syncthreads();
     }
 
     // ---- running term M = B[r-1] + P[r] (+ leak); B[0] = 0 so M starts as P[1]. The only loop-carried registers. ----
@@ -466,6 +473,7 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
                 if (r + kAhead - 1 < n) coop_store(r + kAhead - 1, pre);
                 if (r + kAhead < n) coop_load(r + kAhead, pre);
             }
+            if ((patch_left || patch_right) && r + 2 < n) { await_row(r + 2); patch_row(r + 2); }
         }
         uint32_t wb[4];                                  // K[r]: upper row of the pair whose costs are formed, lower row of the interpolation
         Taps Tb;

@@ -12,6 +12,8 @@ import numpy as np
 import torch
 import bench
 from pysangnom import cuda
+if os.environ.get("SANGNOM_DEV_LIB"):       # kernel experiments: a library built aside (never the product path)
+    cuda.CUDA_LIB = os.path.abspath(os.environ["SANGNOM_DEV_LIB"])
 from pysangnom.clips import make_frame
 from pysangnom.formats import FORMATS
 
