@@ -379,8 +379,12 @@ sangnom_u8_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, int 
     uint32_t M[kNumCost][4];
 
     // Stale costs of pool row `row` for my columns: what the previous pass of the frame left there.
+    // (P[row] enters L[row-1] and L[row]; past the dependency cone of pool row `row - 1` no output of the frame can see
+    // either, so those cells are not fetched at all: a warp stays until its FIRST column leaves the cone, this trims the
+    // threads of its last rows that are already outside)
     auto stale_costs = [&](int row, uint32_t (&Pb)[kNumCost][2]) {
-        const StateRow in = state_row(t.in, row, x0, S);
+        StateRow in = state_row(t.in, row, x0, S);
+        if (x0 >= t.cone - 3 * (row - 1)) in.p = nullptr;
 #pragma unroll
         for (int i = 0; i < kNumCost; ++i) {
             const uint2 v = in.p != nullptr ? __ldg(reinterpret_cast<const uint2*>(in.p + i * in.stride)) : make_uint2(0u, 0u);
