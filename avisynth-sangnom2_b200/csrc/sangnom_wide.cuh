@@ -93,16 +93,6 @@ __device__ __forceinline__ void from_words(const uint4 q, float (&v)[4])
 __device__ __forceinline__ uint32_t word_of(int v) { return (uint32_t)v; }
 __device__ __forceinline__ uint32_t word_of(float v) { return __float_as_uint(v); }
 
-// Replicate the picture edges inside a window of samples x0-4 .. x0+7 (reference loadPixel :25-34).
-template <typename I>
-__device__ __forceinline__ void fix_edges(I (&w)[kWin], int x0, int W)
-{
-    if (x0 == 0) { w[0] = w[4]; w[1] = w[4]; w[2] = w[4]; w[3] = w[4]; }
-    const int last = W - 1 - (x0 - 4);          // window index of the last picture column (>= 4 for a thread with pixels)
-#pragma unroll
-    for (int e = 5; e < kWin; ++e) if (e > last) w[e] = w[e - 1];
-}
-
 // Where the cost state of one pool row lives for this thread's 4 columns: samples of buffer i at p + i * stride.
 // p == nullptr: outside the handed-over regions (reads as the zero-filled pool, nothing to write).
 template <typename T> struct StateRow { T* p; size_t stride; };
@@ -240,7 +230,26 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
         if (kClustered && seg_last) *reinterpret_cast<V*>(s + 4) = v[2];
     };
     auto await_row = [&](int slot, unsigned parity) { if (bulk) stage::mbar_wait(&mbar[slot], parity); };
-    // my window of the kept row in `slot` (samples x0-4 .. x0+7) out of the ring, picture edges replicated
+    // Picture edges (reference loadPixel :25-34: sample 0 and sample W-1 replicated outwards) are made in the staged row
+    // itself, once, by the threads whose window holds an edge, right after they have seen the row land and before they
+    // read it: every position a thread ever reads of a kept row (window x0-4 .. x0+7, interpolation operands x0-3 ..
+    // x0+6) lies inside its own window, so each edge thread fixes what it will read and nobody waits for anybody; where
+    // two right-edge threads overlap (W not a multiple of 4) they write the same value. After that neither the windows
+    // nor the indexed operand fetch of the interpolation know about edges. The positions left of 0 are never written by
+    // a bulk copy; those right of W-1 only when W is not a multiple of 16 bytes (then the next copy into the slot is
+    // ordered behind these stores by a proxy fence).
+    auto patch_edges = [&](int slot) {
+        T* const s = slot_ptr(slot) + kPadS + lx;                   // my sample x0
+        if (x0 == 0) { const T v = s[0]; s[-4] = v; s[-3] = v; s[-2] = v; s[-1] = v; }
+        const int last = W - 1 - x0;                                // my index of the last picture sample (>= 0)
+        if (last < 7) {
+            const T v = s[last];
+#pragma unroll
+            for (int e = 1; e < 8; ++e) if (e > last) s[e] = v;
+            if (wpad != W) stage::fence_generic_to_async();
+        }
+    };
+    // my window of the kept row in `slot` (samples x0-4 .. x0+7) out of the ring (edges: see patch_edges)
     auto window = [&](int slot, I (&w)[kWin]) {
         const T* s = slot_ptr(slot) + kPadS + lx;
         I a[4], b[4], c[4];
@@ -249,7 +258,6 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
         unpack4(*reinterpret_cast<const V*>(s + 4), c);
 #pragma unroll
         for (int e = 0; e < 4; ++e) { w[e] = a[e]; w[4 + e] = b[e]; w[8 + e] = c[e]; }
-        if (edge) fix_edges(w, x0, W);
     };
     // 3-tap values of a kept row for my 4 columns: f = T3(x-1, x, x+1), b = T3(x+1, x, x-1). As the upper row of a
     // pair they are (f1, b1), as the lower row (f2, b2) = (b, f) (reference :103-106).
@@ -357,6 +365,7 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
             I wa[kWin], wb[kWin];
             Tap3 ta, tb;
             await_row(0, 0u);
+            if (edge) patch_edges(0);
             window(0, wa);
             tap3_row(wa, ta);
             t3_put(0, ta);
@@ -368,6 +377,7 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
                 if (t.copy_kept) store4(t.offset, pack4(own, T()));
             } else {
                 await_row(1, 0u);
+                if (edge) patch_edges(1);
                 window(1, wb);
                 tap3_row(wb, tb);
                 t3_put(1, tb);
@@ -382,15 +392,10 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
     // Threads without (all) pixel columns read the cost state the previous pass handed over every row (prefetched a row
     // ahead, see prefetch_stale).
 #ifdef SN_HOST_EMULATION
-    bool warp_full = true, warp_edge = false;
-    for (int l = wfirst; l <= wlast; ++l) {
-        const int lx0 = seg_x0 + l * kCols, lnp = min(max(W - lx0, 0), kCols);
-        warp_full = warp_full && lnp == kCols;
-        warp_edge = warp_edge || (lnp > 0 && (lx0 == 0 || lx0 + 7 > W - 1));
-    }
+    bool warp_full = true;
+    for (int l = wfirst; l <= wlast; ++l) warp_full = warp_full && min(max(W - (seg_x0 + l * kCols), 0), kCols) == kCols;
 #else
     const bool warp_full = __all_sync(0xFFFFFFFFu, npix == kCols);
-    const bool warp_edge = __any_sync(0xFFFFFFFFu, edge);
 #endif
     if (!warp_full) prefetch_stale(2);
     // all blocks of a cluster run, with their halo barriers initialised, before the first DSMEM store
@@ -440,6 +445,7 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
                 window(s0, wb);
                 t3_get(ph3, tb);
                 await_row(s1, par1);
+                if (edge) patch_edges(s1);
                 window(s1, wc);
                 tap3_row(wc, tc);
                 t3_put(ph3_next, tc);
@@ -549,30 +555,18 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
             t3_get(ph3_prev, tu);
             t3_get(ph3, td);
             I px[kCols];
-            // the winning direction's operands, fetched by index; a warp with a picture edge in it clamps the taps
-            // (loadPixel :25-34) - a warp-uniform choice made once per row, not per pixel
-            auto interpolate = [&](auto clamped) {
+            // the winning direction's two operands, fetched by index (the staged rows carry their replicated edges)
 #pragma unroll
-                for (int c = 0; c < kCols; ++c) {
-                    int rank;
-                    if constexpr (kFloat) rank = fmin[c] > thr_f ? 0 : frank[c];
-                    else rank = kmin[c] & 15;
-                    const int d3 = tap_index(rank);                         // d + 3
-                    I a, b;
-                    if constexpr (decltype(clamped)::value) {
-                        const int xa = min(max(x0 + c + d3 - 3, 0), W - 1), xb = min(max(x0 + c + 3 - d3, 0), W - 1);
-                        a = (I)(up + 3 - x0)[xa];
-                        b = (I)(dn - 3 - x0)[xb];
-                    } else {
-                        a = (I)up[c + d3];
-                        b = (I)dn[c - d3];
-                    }
-                    if (rank == 1) { a = tu.b[c]; b = td.f[c]; }
-                    if (rank == 2) { a = tu.f[c]; b = td.b[c]; }
-                    px[c] = mean2(a, b);
-                }
-            };
-            if (warp_edge) interpolate(std::true_type{}); else interpolate(std::false_type{});
+            for (int c = 0; c < kCols; ++c) {
+                int rank;
+                if constexpr (kFloat) rank = fmin[c] > thr_f ? 0 : frank[c];
+                else rank = kmin[c] & 15;
+                const int d3 = tap_index(rank);                             // d + 3
+                I a = (I)up[c + d3], b = (I)dn[c - d3];
+                if (rank == 1) { a = tu.b[c]; b = td.f[c]; }
+                if (rank == 2) { a = tu.f[c]; b = td.b[c]; }
+                px[c] = mean2(a, b);
+            }
             const int y = t.offset + 2 * (r - 1);
             store4(y + 1, pack4(px, T()));
             if (t.copy_kept) store4(y, own4(sm1));
@@ -621,6 +615,7 @@ sangnom_wide_row_sweep(const PlaneTask* __restrict__ tasks, LaunchGeometry g, in
             advance();
         }
     };
+    // warp-uniform choice, so that a warp never splits over the copies of the row barrier
     // warp-uniform choice, so that a warp never splits over the copies of the row barrier
     if (warp_full) sweep(std::true_type{}); else sweep(std::false_type{});
 #ifdef SN_HOST_EMULATION
