@@ -121,6 +121,22 @@ def test_cluster_split_matches_oracle(emul, fmtname, w, h, kw, cluster):
     assert_planes_equal(got, exp[:3], f"{fmtname} {w}x{h} {kw} G={cluster}")
 
 
+# The picture's right edge one to three columns into the second block of a cluster (the first block's last thread
+# then needs the replicated edge in ITS staged rows, and for 4-column threads two threads share it), and next to the
+# end of the pool; every sample width.
+SEGMENT_EDGE_CASES = [(f, w, 12, 2) for f in ("Y8", "Y16", "Y32") for w in (33, 34, 35, 61, 62, 63)] + [("YV411", 4 * w, 16, 2) for w in (33, 34, 35)]
+
+
+@pytest.mark.parametrize("fmtname,w,h,cluster", SEGMENT_EDGE_CASES, ids=[f"{c[0]}_{c[1]}x{c[2]}_G{c[3]}" for c in SEGMENT_EDGE_CASES])
+def test_picture_edge_near_a_segment_boundary(emul, fmtname, w, h, cluster):
+    fmt = FORMATS[fmtname]
+    for kind in ("noise", "edges"):
+        fr = make_frame(43, w, h, fmt, kind, 0)
+        got = emulate(emul, fr, fmt.bits, cluster=cluster, order=1, aa=48, aac=48)
+        exp = O.oracle_frame(fr, fmt.bits, order=1, aa=48, aac=48)
+        assert_planes_equal(got, exp[:3], f"{fmtname} {w}x{h} {kind} G={cluster}")
+
+
 PERSISTENT_CASES = [("Y8", 40, 12, dict(order=1), 1), ("YV12", 100, 48, dict(order=0, aa=48, aac=48), 1), ("YV12", 72, 40, dict(luma=False, aa=48, aac=48), 1),
                     ("YV12", 96, 64, dict(chroma=False), 1), ("YV24", 44, 20, dict(dh=True, aa=48, aac=48), 1), ("YUV420P16", 100, 40, dict(order=2, aa=48, aac=20), 1),
                     ("Y32", 40, 12, dict(order=1), 1), ("YUV422PS", 68, 30, dict(order=1, aa=10, aac=30), 1), ("YV12", 250, 36, dict(order=0, aa=48, aac=48), 4),
