@@ -8,6 +8,7 @@
 #pragma once
 
 #include <cstdint>
+#include <deque>
 #include <map>
 #include <mutex>
 #include <unordered_map>
@@ -29,23 +30,25 @@ class SangNom2 : public GenericVideoFilter {
     sn_ctx* ctx_ = nullptr;
     int batch_frames_;        // frames fetched and processed per cache miss on sequential access
     int last_request_ = -2;
-    bool prefetch_ = true;    // submit the next batch while the host consumes the finished one
+    int prefetch_depth_ = 2;  // batches submitted ahead of the one the host is consuming (0 = none)
     std::map<int, PVideoFrame> ready_;   // finished frames not yet (or recently) served
     std::mutex mu_;
 
-    // A batch that has been submitted to the device but not waited for yet: while the host consumes the frames of
-    // batch k, batch k+1 is already uploading / running (sangnom_cuda_submit / _wait).
+    // Batches that have been submitted to the device but not waited for yet, oldest first: while the host consumes the
+    // frames of batch k, batch k+1 is running and batch k+2 uploading (sangnom_cuda_submit / _wait) - with one batch
+    // ahead only, the device pipeline drains between batches whenever the consumer is faster than a batch's latency.
     struct Pending {
-        bool active = false;
         int first = 0, count = 0;
         sn_ticket ticket = 0;
         std::vector<PVideoFrame> srcs, dsts;   // keep the frame buffers alive until the batch is waited for
-    } pending_;
+    };
+    std::deque<Pending> pending_;
 
     // Frame buffers the host keeps recycling (AviSynth+'s frame registry hands the same VideoFrameBuffers out again
     // and again) are pinned for DMA the second time they are seen, so that their planes travel without the staging
-    // copies of pageable memory; least recently used ones are unpinned when the budget is exceeded. Only ever touched
-    // while no batch is in flight. SANGNOM_B200_PIN_MB=0 switches it off (see INTEGRATION.md for when to do that).
+    // copies of pageable memory; least recently used ones are unpinned when the budget is exceeded - only buffers that
+    // have not been handed to the filter for many batches, so never one a batch in flight still uses.
+    // SANGNOM_B200_PIN_MB=0 switches it off (see INTEGRATION.md for when to do that).
     struct PinEntry { size_t bytes = 0; int seen = 0; uint64_t last_use = 0; bool pinned = false; };
     std::unordered_map<const void*, PinEntry> pins_;
     size_t pinned_bytes_ = 0, pin_budget_ = 0, pin_min_bytes_ = 0;
@@ -54,7 +57,7 @@ class SangNom2 : public GenericVideoFilter {
 
     int field_offset(int n);
     void start_batch(int first, int count, IScriptEnvironment* env);
-    void finish_batch(IScriptEnvironment* env);
+    void finish_oldest_batch(int wanted, IScriptEnvironment* env);
 
 public:
     SangNom2(PClip _child, int order, int aa, int aac, int threads, bool dh, bool luma, bool chroma, int opt, IScriptEnvironment* env);

@@ -84,8 +84,11 @@ SangNom2::SangNom2(PClip _child, int order, int aa, int aac, int threads, bool d
     // widths that are not a multiple of 32, luma=false with subsampled chroma). Frames then run one after another.
     if (env_int("SANGNOM_B200_PERSISTENT", 0, 0, 1)) cfg.flags |= SN_FLAG_PERSISTENT_POOL;
     if (opt == 1 || (opt < 0 && (env->GetCPUFlags() & CPUF_SSE2))) cfg.flags |= SN_FLAG_SATURATE;
-    // SANGNOM_B200_PREFETCH=0: no speculative next batch (every child frame is requested only when it is needed)
-    prefetch_ = env_int("SANGNOM_B200_PREFETCH", 1, 0, 1) != 0;
+    // SANGNOM_B200_PREFETCH: batches submitted ahead on sequential reads. 0: none (every child frame is requested only
+    // when it is needed); 1: the next batch runs while the host consumes the finished one; 2 (default): one more
+    // behind it, so that its upload overlaps the kernels and the download of the batch before - a consumer faster than
+    // a batch's latency (a benchmark, a fast encoder) otherwise sees the device pipeline drain after every batch.
+    prefetch_depth_ = env_int("SANGNOM_B200_PREFETCH", 2, 0, 4);
     // SANGNOM_B200_PIN_MB: budget for pinning the host's recycled frame buffers (0 = never). Unset: 2 GB, and only frame
     // buffers of 16 MB and more are pinned - pinning costs ~4 ms per buffer whatever its size, once, which a few dozen
     // large buffers repay (+5 % frames/s at 2160p fp32) and a few hundred small ones do not (+2 % at 1080p 8-bit
@@ -98,11 +101,11 @@ SangNom2::SangNom2(PClip _child, int order, int aa, int aac, int threads, bool d
 
 SangNom2::~SangNom2()
 {
-    if (pending_.active) sangnom_cuda_wait(ctx_, pending_.ticket);     // nothing may still write into the frames
+    for (const Pending& p : pending_) sangnom_cuda_wait(ctx_, p.ticket);   // nothing may still write into the frames
     for (auto& kv : pins_)
         if (kv.second.pinned) sangnom_cuda_host_unpin(ctx_, const_cast<void*>(kv.first));
     pins_.clear();
-    pending_ = Pending{};
+    pending_.clear();
     ready_.clear();
     sangnom_cuda_destroy(ctx_);
 }
@@ -152,8 +155,9 @@ int SangNom2::field_offset(int n)
 
 void SangNom2::start_batch(int first, int count, IScriptEnvironment* env)
 {
-    std::vector<PVideoFrame>& srcs = pending_.srcs;
-    std::vector<PVideoFrame>& dsts = pending_.dsts;
+    Pending batch;
+    std::vector<PVideoFrame>& srcs = batch.srcs;
+    std::vector<PVideoFrame>& dsts = batch.dsts;
     srcs.assign((size_t)count, PVideoFrame());
     dsts.assign((size_t)count, PVideoFrame());
     std::vector<sn_plane_job> jobs;
@@ -202,23 +206,25 @@ void SangNom2::start_batch(int first, int count, IScriptEnvironment* env)
         }
     }
     // the job array is copied by the library; the frames themselves stay referenced in pending_
-    if (sangnom_cuda_submit(ctx_, jobs.data(), (int)jobs.size(), &pending_.ticket) != SN_OK) {
-        pending_ = Pending{};
+    if (sangnom_cuda_submit(ctx_, jobs.data(), (int)jobs.size(), &batch.ticket) != SN_OK)
         env->ThrowError("SangNom2: %s", sangnom_cuda_last_error(ctx_));
-    }
-    pending_.active = true;
-    pending_.first = first;
-    pending_.count = count;
+    batch.first = first;
+    batch.count = count;
+    pending_.push_back(std::move(batch));
 }
 
-void SangNom2::finish_batch(IScriptEnvironment* env)
+// Wait for the oldest batch in flight and file its frames. A failed batch fails this call only if it holds the frame
+// being asked for (`wanted`); otherwise its frames are simply not there and are computed again when somebody asks.
+void SangNom2::finish_oldest_batch(int wanted, IScriptEnvironment* env)
 {
-    if (!pending_.active) return;
-    const int rc = sangnom_cuda_wait(ctx_, pending_.ticket);
+    if (pending_.empty()) return;
+    Pending p = std::move(pending_.front());
+    pending_.pop_front();
+    const int rc = sangnom_cuda_wait(ctx_, p.ticket);
     if (rc == SN_OK)
-        for (int k = 0; k < pending_.count; ++k) ready_[pending_.first + k] = pending_.dsts[(size_t)k];
-    pending_ = Pending{};
-    if (rc != SN_OK) env->ThrowError("SangNom2: %s", sangnom_cuda_last_error(ctx_));
+        for (int k = 0; k < p.count; ++k) ready_[p.first + k] = p.dsts[(size_t)k];
+    else if (wanted >= p.first && wanted < p.first + p.count)
+        env->ThrowError("SangNom2: %s", sangnom_cuda_last_error(ctx_));
 }
 
 PVideoFrame __stdcall SangNom2::GetFrame(int n, IScriptEnvironment* env)
@@ -232,40 +238,46 @@ PVideoFrame __stdcall SangNom2::GetFrame(int n, IScriptEnvironment* env)
             if (ready_.count(first + k)) { count = k; break; }     // frames already finished are not recomputed
         return count < 1 ? 0 : count;
     };
+    auto in_flight = [&](int f) {
+        for (const Pending& p : pending_)
+            if (f >= p.first && f < p.first + p.count) return true;
+        return false;
+    };
     auto hit = ready_.find(n);
     if (hit == ready_.end()) {
-        if (pending_.active && n >= pending_.first && n < pending_.first + pending_.count) {
-            finish_batch(env);                          // the prefetched batch holds it
+        if (in_flight(n)) {
+            while (ready_.find(n) == ready_.end() && !pending_.empty()) finish_oldest_batch(n, env);   // a prefetched batch holds it
         } else {
-            finish_batch(env);                          // one batch in flight at a time
-            hit = ready_.find(n);
-            if (hit == ready_.end()) {
-                // Sequential pulls (the normal frameserver pattern) are served in batches so the GPU sees
-                // many planes per launch; a seek falls back to a single frame.
-                const bool sequential = (n == last_request_ + 1) || (n == 0 && last_request_ == -2);
-                int count = window(n, sequential ? batch_frames_ : 1);
-                if (count < 1) count = 1;
-                start_batch(n, count, env);
-                finish_batch(env);
-            }
+            while (!pending_.empty()) finish_oldest_batch(n, env);     // a seek: what is in flight comes home first
         }
         hit = ready_.find(n);
+        if (hit == ready_.end()) {
+            // Sequential pulls (the normal frameserver pattern) are served in batches so the GPU sees
+            // many planes per launch; a seek falls back to a single frame.
+            const bool sequential = (n == last_request_ + 1) || (n == 0 && last_request_ == -2);
+            int count = window(n, sequential ? batch_frames_ : 1);
+            if (count < 1) count = 1;
+            while (!pending_.empty()) finish_oldest_batch(n, env);
+            start_batch(n, count, env);
+            finish_oldest_batch(n, env);
+            hit = ready_.find(n);
+        }
     }
     PVideoFrame out = hit->second;
     const bool sequential = (n == last_request_ + 1) || (n == 0 && last_request_ == -2);
     last_request_ = n;
-    // Prefetch: on a sequential read the batch after the finished run is submitted right away, so that it uploads and
-    // runs while the host consumes (encodes, filters further) what is ready.
-    if (sequential && !pending_.active && prefetch_) {
-        int next = n + 1;
+    // Prefetch: on a sequential read the batches after the finished run are submitted ahead (one new batch per call),
+    // so that they upload and run while the host consumes (encodes, filters further) what is ready.
+    if (sequential && (int)pending_.size() < prefetch_depth_) {
+        int next = (pending_.empty() ? n : pending_.back().first + pending_.back().count - 1) + 1;
         while (ready_.count(next)) ++next;
-        if (next <= last && next - n <= batch_frames_) {
+        if (next <= last && next - n <= prefetch_depth_ * batch_frames_) {
             const int count = window(next, batch_frames_);
             // Frame n is finished: a failure while fetching or submitting LATER frames must not fail this call. The
             // prefetch is dropped and the error surfaces when one of those frames is actually requested.
             if (count > 0) {
                 try { start_batch(next, count, env); }
-                catch (...) { pending_ = Pending{}; }
+                catch (...) {}
             }
         }
     }

@@ -196,10 +196,11 @@ def test_batched_prefetch_and_seek(monkeypatch):
 
 
 def test_next_batch_is_prefetched_asynchronously(monkeypatch):
-    """Default mode: after a sequential miss the following batch is submitted at once (sangnom_cuda_submit) and waited
-    for only when one of its frames is pulled; seeks, the clip end and the filter's destruction with a batch in flight
-    all keep the output exact."""
+    """One batch ahead: after a sequential miss the following batch is submitted at once (sangnom_cuda_submit) and
+    waited for only when one of its frames is pulled; seeks, the clip end and the filter's destruction with a batch in
+    flight all keep the output exact."""
     monkeypatch.setenv("SANGNOM_B200_BATCH", "4")
+    monkeypatch.setenv("SANGNOM_B200_PREFETCH", "1")
     fmt = FORMATS["YUV420P8"]
     w, h, n = 96, 64, 19
     frames = [make_frame(8, w, h, fmt, "noise", i) for i in range(n)]
@@ -221,6 +222,39 @@ def test_next_batch_is_prefetched_asynchronously(monkeypatch):
         for i in range(4, 12):
             assert_planes_equal(flt.get_frame(i)[:3], exp[i][:3], f"frame {i} again")
         # leave with a batch in flight: the destructor must wait for it
+
+
+def test_two_batches_ahead_by_default(monkeypatch):
+    """Default mode: two batches are kept in flight behind the one being served (one new batch per GetFrame call), in
+    frame order; seeks across them, reading to the clip end and leaving with two batches in flight stay exact."""
+    monkeypatch.setenv("SANGNOM_B200_BATCH", "4")
+    fmt = FORMATS["YUV420P8"]
+    w, h, n = 96, 64, 31
+    frames = [make_frame(12, w, h, fmt, "noise", i) for i in range(n)]
+    exp = [O.oracle_frame(fr, 8, order=0, aa=48, aac=48, parity=parity_of(i)) for i, fr in enumerate(frames)]
+    with FakeHost(cpu_flags=0) as host:
+        host.load_plugin(OURS)
+        src = host.source(w, h, fmt, n, parity_mode=2)
+        for i, fr in enumerate(frames):
+            src.set_frame(i, fr)
+        flt = host.invoke("SangNom2", src, order=0, aa=48, aac=48)
+        assert_planes_equal(flt.get_frame(0)[:3], exp[0][:3], "frame 0")
+        assert src.requests() == list(range(8))                     # batch 0 finished, batch 1 in flight
+        assert_planes_equal(flt.get_frame(1)[:3], exp[1][:3], "frame 1")
+        assert src.requests() == list(range(12))                    # ... and batch 2 behind it
+        for i in range(2, 4):
+            assert_planes_equal(flt.get_frame(i)[:3], exp[i][:3], f"frame {i}")
+        assert src.requests() == list(range(12))                    # never more than two ahead
+        for i in range(4, 14):
+            assert_planes_equal(flt.get_frame(i)[:3], exp[i][:3], f"frame {i}")
+        assert src.requests() == sorted(src.requests()) and len(set(src.requests())) == len(src.requests())   # in order, nothing fetched twice
+        assert_planes_equal(flt.get_frame(29)[:3], exp[29][:3], "seek forward over two batches in flight")
+        assert_planes_equal(flt.get_frame(30)[:3], exp[30][:3], "last frame")
+        assert_planes_equal(flt.get_frame(16)[:3], exp[16][:3], "a frame of a batch that was in flight during the seek")
+        assert_planes_equal(flt.get_frame(2)[:3], exp[2][:3], "seek back")
+        for i in range(3, 12):
+            assert_planes_equal(flt.get_frame(i)[:3], exp[i][:3], f"frame {i} again")
+        # leave with two batches in flight: the destructor must wait for both
 
 
 def test_prefetch_failure_does_not_fail_a_finished_frame(monkeypatch):
